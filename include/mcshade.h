@@ -1,0 +1,165 @@
+/*
+ * mcshade.h -- C ABI of libmcshade.so, the B200-native (sm_100a) replacement for the nvdiffrecmc
+ * per-iteration hot path.  No torch / pybind types cross this boundary: plain device pointers,
+ * sizes, element strides and a CUDA stream handle.  Every entry point returns 0 on success and a
+ * non-zero code on failure (mcs_last_error() then holds a message); unlike the reference
+ * (render/optixutils/c_src/common.h:37-61, errors formatted then dropped) nothing fails silently.
+ * All work is enqueued on `stream` and NO entry point synchronises the host (the reference forces a
+ * cudaStreamSynchronize after every env_shade launch, optixutils/c_src/torch_bindings.cpp:185,269).
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the reference
+ * repository root).
+ */
+#ifndef MCSHADE_H
+#define MCSHADE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCS_ABI_VERSION 1
+
+/* Strided NHWC view of fp32 (or int32) device memory.  sizes/strides are in ELEMENTS, dims are
+ * (N, H, W, C); a size-1 dimension broadcasts (stride ignored), exactly like the reference's
+ * accessors (optixutils/c_src/common.h:13-27 fetch3; renderutils/c_src/tensor.h:32 nhwcIndex). */
+typedef struct mcs_tensor {
+    const void *ptr;
+    int32_t sizes[4];
+    int32_t strides[4];
+} mcs_tensor;
+
+typedef struct mcs_ctx mcs_ctx;       /* opaque; replaces OptiXStateWrapper (optixutils/c_src/optix_wrapper.h:17-37) */
+typedef void *mcs_stream;             /* cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------- */
+int mcs_abi_version(void);
+const char *mcs_last_error(void);     /* thread-local message of the last failing call */
+
+/* ---- context: replaces OptiXStateWrapper(path, cuda_home) ctor/dtor,
+ *      optixutils/c_src/optix_wrapper.cpp:306-348 (no NVRTC, no OptiX: nothing to compile at run time) */
+int mcs_ctx_create(mcs_ctx **out);
+int mcs_ctx_destroy(mcs_ctx *ctx);
+
+/* ---- acceleration structure: replaces optix_build_bvh(state, verts, tris, rebuild),
+ *      optixutils/c_src/torch_bindings.cpp:37-116 (optixAccelBuild).
+ *      verts: V x 3 fp32 contiguous, tris: T x 3 int32 contiguous (device).  rebuild != 0: full LBVH
+ *      build (Morton sort + Karras topology + refit); rebuild == 0: refit boxes on the existing
+ *      topology (OPTIX_BUILD_OPERATION_UPDATE).  Runs on `stream` (the reference uses stream 0). */
+int mcs_bvh_build(mcs_ctx *ctx, const float *verts, int32_t V, const int32_t *tris, int32_t T, uint32_t rebuild, mcs_stream stream);
+
+/* Test / inspection hook: copies the binary LBVH (sorted Morton keys, sorted->original triangle
+ * ids, Karras children, padded node boxes) into caller-provided DEVICE buffers of sizes
+ * T, T, T-1, T-1, (2T-1)*3, (2T-1)*3.  Node ids: internal 0..T-2, leaf j = T-1+j. */
+int mcs_bvh_export(mcs_ctx *ctx, uint32_t *morton, int32_t *prim, int32_t *left, int32_t *right, float *lo, float *hi, mcs_stream stream);
+
+/* Any-hit visibility of n rays (origin, direction; t in (0, 1e16)), the "integer visibility mask":
+ * vis[i] = 1 if nothing is hit.  Same predicate as the shadow rays inside env_shade; replaces
+ * shadow_test()/optixTrace, optixutils/c_src/envsampling/kernel.cu:101-118. */
+int mcs_trace_visibility(mcs_ctx *ctx, const float *ro, const float *rd, int64_t n, uint8_t *vis, mcs_stream stream);
+
+/* Closest hit (primary visibility for the synthetic G-buffer producer):
+ * tri_id[i] = original triangle id or -1; tuv[i] = (t, u, v). */
+int mcs_trace_closest(mcs_ctx *ctx, const float *ro, const float *rd, int64_t n, int32_t *tri_id, float *tuv, mcs_stream stream);
+
+/* ---- fused env-light importance sampling + shadow rays + BSDF:
+ *      replaces env_shade_fwd / env_shade_bwd, optixutils/c_src/torch_bindings.cpp:123-188 / 190-272
+ *      (optixLaunch of __raygen__rg, envsampling/kernel.cu:463-542).
+ *      mask [B,H,W,1]; ro, gb_pos, gb_normal, gb_kd, gb_ks [B,H,W,3]; gb_view_pos broadcastable
+ *      [B|1,H|1,W|1,3]; light [1,Hl,Wl,3]; pdf [1,Hl,Wl,1]; rows [1,Hl,1,1]; cols [1,Hl,Wl,1];
+ *      perms int32 [1,P,1,N*N] (all as mcs_tensor views, arbitrary strides).
+ *      bsdf: 0 'pbr', 1 'diffuse', 2 'white' (optixutils/ops.py:136).
+ *      batch_offset is added to the batch index inside the per-pixel RNG hash so a rank that holds
+ *      views [o, o+B) of a larger batch reproduces the single-GPU random stream (kernel.cu:504).
+ *      Outputs are contiguous [B,H,W,3] fp32 and are fully written (masked pixels = 0). */
+int mcs_env_shade_fwd(mcs_ctx *ctx,
+                      const mcs_tensor *mask, const mcs_tensor *ro, const mcs_tensor *gb_pos, const mcs_tensor *gb_normal,
+                      const mcs_tensor *gb_view_pos, const mcs_tensor *gb_kd, const mcs_tensor *gb_ks,
+                      const mcs_tensor *light, const mcs_tensor *pdf, const mcs_tensor *rows, const mcs_tensor *cols,
+                      const mcs_tensor *perms,
+                      uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
+                      float *diff, float *spec, mcs_stream stream);
+
+/* Gradient outputs: gb_pos_grad, gb_normal_grad, gb_kd_grad, gb_ks_grad contiguous [B,H,W,3]
+ * (fully written), light_grad contiguous [Hl,Wl,3] (zeroed by the call, then accumulated). */
+int mcs_env_shade_bwd(mcs_ctx *ctx,
+                      const mcs_tensor *mask, const mcs_tensor *ro, const mcs_tensor *gb_pos, const mcs_tensor *gb_normal,
+                      const mcs_tensor *gb_view_pos, const mcs_tensor *gb_kd, const mcs_tensor *gb_ks,
+                      const mcs_tensor *light, const mcs_tensor *pdf, const mcs_tensor *rows, const mcs_tensor *cols,
+                      const mcs_tensor *perms,
+                      uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
+                      const mcs_tensor *diff_grad, const mcs_tensor *spec_grad,
+                      float *gb_pos_grad, float *gb_normal_grad, float *gb_kd_grad, float *gb_ks_grad, float *light_grad,
+                      mcs_stream stream);
+
+/* Debug/parity hook: forward pass that also records, per pixel and per ray slot
+ * (slot = 2*i for the light sample of stratum i, 2*i+1 for the BSDF sample), the env texel read
+ * ((y<<16)|x) and the shadow-ray result (1 visible, 0 occluded; 255/-1 for masked pixels).
+ * rec_texel int32 [B,H,W,2N^2], rec_vis uint8 [B,H,W,2N^2].  Rays whose contribution is provably
+ * zero are not traced by the product; their rec_vis is 2 ("skipped"). */
+int mcs_env_shade_records(mcs_ctx *ctx,
+                          const mcs_tensor *mask, const mcs_tensor *ro, const mcs_tensor *gb_pos, const mcs_tensor *gb_normal,
+                          const mcs_tensor *gb_view_pos, const mcs_tensor *gb_kd, const mcs_tensor *gb_ks,
+                          const mcs_tensor *light, const mcs_tensor *pdf, const mcs_tensor *rows, const mcs_tensor *cols,
+                          const mcs_tensor *perms,
+                          uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
+                          float *diff, float *spec, int32_t *rec_texel, uint8_t *rec_vis, mcs_stream stream);
+
+/* ---- bilateral denoiser: replaces bilateral_denoiser_fwd / _bwd,
+ *      optixutils/c_src/torch_bindings.cpp:274-319 (denoising.cu:14-130).
+ *      col, nrm [B,H,W,3], zdz [B,H,W,2] strided views; out contiguous [B,H,W,4]
+ *      = (sum w*col, max(sum w, 1e-4)); col_grad contiguous [B,H,W,3]; out_grad [B,H,W,4] view. */
+int mcs_bilateral_fwd(const mcs_tensor *col, const mcs_tensor *nrm, const mcs_tensor *zdz, float sigma, float *out, mcs_stream stream);
+int mcs_bilateral_bwd(const mcs_tensor *nrm, const mcs_tensor *zdz, float sigma, const mcs_tensor *out_grad, float *col_grad, mcs_stream stream);
+/* Fused fast path for the two calls render/render.py:120-121 makes with identical guides
+ * (diffuse + specular): weights are computed once.  outA/outB as above. */
+int mcs_bilateral_fwd2(const mcs_tensor *colA, const mcs_tensor *colB, const mcs_tensor *nrm, const mcs_tensor *zdz, float sigma,
+                       float *outA, float *outB, mcs_stream stream);
+int mcs_bilateral_bwd2(const mcs_tensor *nrm, const mcs_tensor *zdz, float sigma, const mcs_tensor *out_gradA, const mcs_tensor *out_gradB,
+                       float *col_gradA, float *col_gradB, mcs_stream stream);
+
+/* ---- renderutils elementwise ops: replace the *_fwd / *_bwd functions of renderutils_plugin,
+ *      renderutils/c_src/torch_bindings.cpp:866-888.  Inputs are broadcastable NHWC views; the launch
+ *      grid (N,H,W) is the max over inputs (update_grid, torch_bindings.cpp:87-101); outputs and
+ *      gradients are contiguous full-grid fp32 (gradients of broadcast inputs are NOT reduced, as in
+ *      the reference, tensor.h:61,75 -- the autograd wrapper sums them). */
+int mcs_lambert_fwd(const mcs_tensor *nrm, const mcs_tensor *wi, float *out, mcs_stream s);                                   /* torch_bindings.cpp:255 */
+int mcs_lambert_bwd(const mcs_tensor *nrm, const mcs_tensor *wi, const mcs_tensor *d_out, float *d_nrm, float *d_wi, mcs_stream s);
+int mcs_frostbite_fwd(const mcs_tensor *nrm, const mcs_tensor *wi, const mcs_tensor *wo, const mcs_tensor *lin_rough, float *out, mcs_stream s);
+int mcs_frostbite_bwd(const mcs_tensor *nrm, const mcs_tensor *wi, const mcs_tensor *wo, const mcs_tensor *lin_rough, const mcs_tensor *d_out,
+                      float *d_nrm, float *d_wi, float *d_wo, float *d_lin_rough, mcs_stream s);
+int mcs_fresnel_shlick_fwd(const mcs_tensor *f0, const mcs_tensor *f90, const mcs_tensor *cos_theta, float *out, mcs_stream s);
+int mcs_fresnel_shlick_bwd(const mcs_tensor *f0, const mcs_tensor *f90, const mcs_tensor *cos_theta, const mcs_tensor *d_out,
+                           float *d_f0, float *d_f90, float *d_cos, mcs_stream s);
+int mcs_ndf_ggx_fwd(const mcs_tensor *alpha_sqr, const mcs_tensor *cos_theta, float *out, mcs_stream s);
+int mcs_ndf_ggx_bwd(const mcs_tensor *alpha_sqr, const mcs_tensor *cos_theta, const mcs_tensor *d_out, float *d_alpha_sqr, float *d_cos, mcs_stream s);
+int mcs_lambda_ggx_fwd(const mcs_tensor *alpha_sqr, const mcs_tensor *cos_theta, float *out, mcs_stream s);
+int mcs_lambda_ggx_bwd(const mcs_tensor *alpha_sqr, const mcs_tensor *cos_theta, const mcs_tensor *d_out, float *d_alpha_sqr, float *d_cos, mcs_stream s);
+int mcs_masking_smith_fwd(const mcs_tensor *alpha_sqr, const mcs_tensor *cos_i, const mcs_tensor *cos_o, float *out, mcs_stream s);
+int mcs_masking_smith_bwd(const mcs_tensor *alpha_sqr, const mcs_tensor *cos_i, const mcs_tensor *cos_o, const mcs_tensor *d_out,
+                          float *d_alpha_sqr, float *d_cos_i, float *d_cos_o, mcs_stream s);
+int mcs_pbr_specular_fwd(const mcs_tensor *col, const mcs_tensor *nrm, const mcs_tensor *wo, const mcs_tensor *wi, const mcs_tensor *alpha,
+                         float min_roughness, float *out, mcs_stream s);
+int mcs_pbr_specular_bwd(const mcs_tensor *col, const mcs_tensor *nrm, const mcs_tensor *wo, const mcs_tensor *wi, const mcs_tensor *alpha,
+                         float min_roughness, const mcs_tensor *d_out,
+                         float *d_col, float *d_nrm, float *d_wo, float *d_wi, float *d_alpha, mcs_stream s);
+/* pbr_bsdf_fwd / pbr_bsdf_bwd, renderutils/c_src/torch_bindings.cpp:653-722; bsdf: 0 lambert, 1 frostbite */
+int mcs_pbr_bsdf_fwd(const mcs_tensor *kd, const mcs_tensor *arm, const mcs_tensor *pos, const mcs_tensor *nrm, const mcs_tensor *view_pos,
+                     const mcs_tensor *light_pos, float min_roughness, int32_t bsdf, float *out, mcs_stream s);
+int mcs_pbr_bsdf_bwd(const mcs_tensor *kd, const mcs_tensor *arm, const mcs_tensor *pos, const mcs_tensor *nrm, const mcs_tensor *view_pos,
+                     const mcs_tensor *light_pos, float min_roughness, int32_t bsdf, const mcs_tensor *d_out,
+                     float *d_kd, float *d_arm, float *d_pos, float *d_nrm, float *d_view_pos, float *d_light_pos, mcs_stream s);
+/* prepare_shading_normal_fwd / _bwd, renderutils/c_src/torch_bindings.cpp:170-250 (normal.cu:95-178) */
+int mcs_prepare_shading_normal_fwd(const mcs_tensor *pos, const mcs_tensor *view_pos, const mcs_tensor *perturbed_nrm, const mcs_tensor *smooth_nrm,
+                                   const mcs_tensor *smooth_tng, const mcs_tensor *geom_nrm, int32_t two_sided_shading, int32_t opengl,
+                                   float *out, mcs_stream s);
+int mcs_prepare_shading_normal_bwd(const mcs_tensor *pos, const mcs_tensor *view_pos, const mcs_tensor *perturbed_nrm, const mcs_tensor *smooth_nrm,
+                                   const mcs_tensor *smooth_tng, const mcs_tensor *geom_nrm, int32_t two_sided_shading, int32_t opengl,
+                                   const mcs_tensor *d_out,
+                                   float *d_pos, float *d_view_pos, float *d_perturbed_nrm, float *d_smooth_nrm, float *d_smooth_tng, float *d_geom_nrm,
+                                   mcs_stream s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCSHADE_H */

@@ -1,0 +1,368 @@
+// bvh.cu -- acceleration-structure build (LBVH) + stand-alone ray queries for sm_100a.
+//
+// Replaces optix_build_bvh -> optixAccelBuild (render/optixutils/c_src/torch_bindings.cpp:37-116),
+// which the training loop calls EVERY iteration (geometry/dlmesh.py:50, dmtet.py:202).  The
+// reference cudaFree/cudaMalloc's its buffers per call and builds on legacy stream 0; here the
+// whole build is 7 small kernels + one radix sort on the caller's stream, no host sync, no
+// allocation in steady state (ctx.h).
+//
+// Pipeline (canonical, bit-identical to oracle/mcoracle.c:orc_lbvh_build so the integer structure
+// can be compared exactly):
+//   1. tri_bounds  : per-triangle AABB + reduction of centroid / scene bounds (order-preserving
+//                    uint encoding + atomicMin/Max, warp-aggregated)
+//   2. morton      : 30-bit Morton code of the AABB centre normalised to the centroid bounds
+//   3. sort        : stable LSD radix sort of (code, triangle id)  [cub::DeviceRadixSort, 30 bits]
+//   4. karras      : Karras-2012 topology, one thread per internal node
+//   5. leaves+refit: padded leaf boxes, sorted triangle records (v0,e1,e2 as 3 x float4), bottom-up
+//                    box union with arrival counters (second thread to arrive continues)
+//   6. emit        : 64-byte traversal nodes holding both children's boxes
+#include <cub/cub.cuh>
+#include "bvh_traverse.cuh"
+#include "ctx.h"
+
+int mcs_buf_reserve(DevBuf &b, size_t bytes, cudaStream_t s)
+{
+    if (bytes <= b.cap) return 0;
+    size_t ncap = b.cap ? b.cap : 256;
+    while (ncap < bytes) ncap *= 2;
+    if (b.p) MCS_CUDA(cudaFreeAsync(b.p, s));
+    b.p = nullptr; b.cap = 0;
+    MCS_CUDA(cudaMallocAsync(&b.p, ncap, s));
+    b.cap = ncap;
+    return 0;
+}
+
+namespace {
+
+// order-preserving float <-> uint mapping for atomicMin/atomicMax
+__device__ __forceinline__ uint32_t f2ord(float f) { uint32_t b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+__device__ __forceinline__ float ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u); }
+
+__global__ void k_bounds_init(uint32_t *bounds)
+{
+    int i = threadIdx.x;
+    if (i < 12) bounds[i] = ((i / 3) & 1) ? 0u : 0xFFFFFFFFu;   // [0..2] cmin, [3..5] cmax, [6..8] smin, [9..11] smax
+}
+
+__global__ void __launch_bounds__(256) k_tri_bounds(const float *__restrict__ verts, const int32_t *__restrict__ tris, int T,
+                                                    float *__restrict__ tlo, float *__restrict__ thi, uint32_t *bounds)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    float c[3] = {0, 0, 0};
+    bool valid = t < T;
+    if (valid) {
+        int i0 = tris[3 * t], i1 = tris[3 * t + 1], i2 = tris[3 * t + 2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float x = verts[3 * (size_t)i0 + a], y = verts[3 * (size_t)i1 + a], z = verts[3 * (size_t)i2 + a];
+            lo[a] = fminf(x, fminf(y, z));
+            hi[a] = fmaxf(x, fmaxf(y, z));
+            c[a] = __fmul_rn(__fadd_rn(lo[a], hi[a]), 0.5f);
+            tlo[3 * (size_t)t + a] = lo[a];
+            thi[3 * (size_t)t + a] = hi[a];
+        }
+    }
+    // warp-aggregated min/max, one atomic per warp per value
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float cmn = valid ? c[a] : INFINITY, cmx = valid ? c[a] : -INFINITY, smn = lo[a], smx = hi[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cmn = fminf(cmn, __shfl_xor_sync(0xFFFFFFFFu, cmn, o));
+            cmx = fmaxf(cmx, __shfl_xor_sync(0xFFFFFFFFu, cmx, o));
+            smn = fminf(smn, __shfl_xor_sync(0xFFFFFFFFu, smn, o));
+            smx = fmaxf(smx, __shfl_xor_sync(0xFFFFFFFFu, smx, o));
+        }
+        if ((threadIdx.x & 31) == 0 && cmn <= cmx) {
+            atomicMin(bounds + a, f2ord(cmn));
+            atomicMax(bounds + 3 + a, f2ord(cmx));
+            atomicMin(bounds + 6 + a, f2ord(smn));
+            atomicMax(bounds + 9 + a, f2ord(smx));
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v)
+{
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_morton(const float *__restrict__ tlo, const float *__restrict__ thi, int T, const uint32_t *__restrict__ bounds,
+                                                uint32_t *__restrict__ keys, int32_t *__restrict__ vals)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    uint32_t q[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float cmin = ord2f(bounds[a]), cmax = ord2f(bounds[3 + a]);
+        float ext = __fsub_rn(cmax, cmin);
+        float c = __fmul_rn(__fadd_rn(tlo[3 * (size_t)t + a], thi[3 * (size_t)t + a]), 0.5f);
+        float n = ext > 0.0f ? __fdiv_rn(__fsub_rn(c, cmin), ext) : 0.0f;
+        int qi = (int)__fmul_rn(n, 1024.0f);
+        q[a] = (uint32_t)min(max(qi, 0), 1023);
+    }
+    keys[t] = (expand_bits10(q[0]) << 2) | (expand_bits10(q[1]) << 1) | expand_bits10(q[2]);
+    vals[t] = t;
+}
+
+__device__ __forceinline__ int lbvh_delta(const uint32_t *__restrict__ k, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    uint32_t a = k[i], b = k[j];
+    if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clz(a ^ b);
+}
+
+// Karras 2012, "Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees"
+__global__ void __launch_bounds__(256) k_karras(const uint32_t *__restrict__ k, int T, int32_t *__restrict__ left, int32_t *__restrict__ right,
+                                                int32_t *__restrict__ parent)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T - 1) return;
+    int d = (lbvh_delta(k, T, i, i + 1) - lbvh_delta(k, T, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = lbvh_delta(k, T, i, i - d);
+    int lmax = 2;
+    while (lbvh_delta(k, T, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (lbvh_delta(k, T, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = lbvh_delta(k, T, i, j);
+    int sp = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (lbvh_delta(k, T, i, i + (sp + t) * d) > dnode) sp += t;
+    } while (t > 1);
+    int gamma = i + sp * d + (d < 0 ? -1 : 0);
+    int lo_ = min(i, j), hi_ = max(i, j);
+    int lc = (lo_ == gamma) ? (T - 1) + gamma : gamma;
+    int rc = (hi_ == gamma + 1) ? (T - 1) + gamma + 1 : gamma + 1;
+    left[i] = lc; right[i] = rc;
+    parent[lc] = i; parent[rc] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+__global__ void __launch_bounds__(256) k_leaves_refit(const float *__restrict__ verts, const int32_t *__restrict__ tris, int T,
+                                                      const float *__restrict__ tlo, const float *__restrict__ thi,
+                                                      const int32_t *__restrict__ prim, const uint32_t *__restrict__ bounds,
+                                                      const int32_t *__restrict__ left, const int32_t *__restrict__ right, const int32_t *__restrict__ parent,
+                                                      float *lo, float *hi, int *flags, float4 *__restrict__ trirec)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= T) return;
+    float ex = __fsub_rn(ord2f(bounds[9]), ord2f(bounds[6]));
+    float ey = __fsub_rn(ord2f(bounds[10]), ord2f(bounds[7]));
+    float ez = __fsub_rn(ord2f(bounds[11]), ord2f(bounds[8]));
+    float pad = __fmul_rn(1e-5f, fmaxf(ex, fmaxf(ey, ez)));
+    int t = prim[j];
+    int node = (T - 1) + j;
+    float l[3], h[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        l[a] = __fsub_rn(tlo[3 * (size_t)t + a], pad);
+        h[a] = __fadd_rn(thi[3 * (size_t)t + a], pad);
+        lo[3 * (size_t)node + a] = l[a];
+        hi[3 * (size_t)node + a] = h[a];
+    }
+    // sorted triangle record
+    {
+        int i0 = tris[3 * t], i1 = tris[3 * t + 1], i2 = tris[3 * t + 2];
+        float ax = verts[3 * (size_t)i0], ay = verts[3 * (size_t)i0 + 1], az = verts[3 * (size_t)i0 + 2];
+        float bx = verts[3 * (size_t)i1], by = verts[3 * (size_t)i1 + 1], bz = verts[3 * (size_t)i1 + 2];
+        float cx = verts[3 * (size_t)i2], cy = verts[3 * (size_t)i2 + 1], cz = verts[3 * (size_t)i2 + 2];
+        trirec[3 * (size_t)j + 0] = make_float4(ax, ay, az, __int_as_float(t));
+        trirec[3 * (size_t)j + 1] = make_float4(__fsub_rn(bx, ax), __fsub_rn(by, ay), __fsub_rn(bz, az), 0.0f);
+        trirec[3 * (size_t)j + 2] = make_float4(__fsub_rn(cx, ax), __fsub_rn(cy, ay), __fsub_rn(cz, az), 0.0f);
+    }
+    if (T == 1) return;
+    // bottom-up: the second thread to reach a node computes its box
+    __threadfence();
+    int p = parent[node];
+    while (p >= 0) {
+        if (atomicAdd(flags + p, 1) == 0) return;
+        __threadfence();
+        int lc = left[p], rc = right[p];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float v0 = __ldcg(lo + 3 * (size_t)lc + a), v1 = __ldcg(lo + 3 * (size_t)rc + a);
+            float w0 = __ldcg(hi + 3 * (size_t)lc + a), w1 = __ldcg(hi + 3 * (size_t)rc + a);
+            lo[3 * (size_t)p + a] = fminf(v0, v1);
+            hi[3 * (size_t)p + a] = fmaxf(w0, w1);
+        }
+        __threadfence();
+        p = parent[p];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_emit_nodes(int T, const int32_t *__restrict__ left, const int32_t *__restrict__ right,
+                                                    const float *__restrict__ lo, const float *__restrict__ hi, float4 *__restrict__ nodes)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (T == 1) {
+        if (i == 0) {   // single triangle: child 0 = the leaf, child 1 = an empty box
+            nodes[0] = make_float4(lo[0], hi[0], lo[1], hi[1]);
+            nodes[1] = make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY);
+            nodes[2] = make_float4(lo[2], hi[2], INFINITY, -INFINITY);
+            nodes[3] = make_float4(__int_as_float(~0), __int_as_float(~0), 0.0f, 0.0f);
+        }
+        return;
+    }
+    if (i >= T - 1) return;
+    int c0 = left[i], c1 = right[i];
+    const float *l0 = lo + 3 * (size_t)c0, *h0 = hi + 3 * (size_t)c0, *l1 = lo + 3 * (size_t)c1, *h1 = hi + 3 * (size_t)c1;
+    nodes[4 * (size_t)i + 0] = make_float4(l0[0], h0[0], l0[1], h0[1]);
+    nodes[4 * (size_t)i + 1] = make_float4(l1[0], h1[0], l1[1], h1[1]);
+    nodes[4 * (size_t)i + 2] = make_float4(l0[2], h0[2], l1[2], h1[2]);
+    int e0 = c0 >= T - 1 ? ~(c0 - (T - 1)) : c0;
+    int e1 = c1 >= T - 1 ? ~(c1 - (T - 1)) : c1;
+    nodes[4 * (size_t)i + 3] = make_float4(__int_as_float(e0), __int_as_float(e1), 0.0f, 0.0f);
+}
+
+__global__ void __launch_bounds__(128) k_visibility(BvhView b, const float *__restrict__ ro, const float *__restrict__ rd, int64_t n, uint8_t *__restrict__ vis)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f3 o = F3(ro[3 * i], ro[3 * i + 1], ro[3 * i + 2]), d = F3(rd[3 * i], rd[3 * i + 1], rd[3 * i + 2]);
+    vis[i] = bvh_occluded(b, o, d) ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(128) k_closest(BvhView b, const float *__restrict__ ro, const float *__restrict__ rd, int64_t n,
+                                                 int32_t *__restrict__ tri_id, float *__restrict__ tuv)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f3 o = F3(ro[3 * i], ro[3 * i + 1], ro[3 * i + 2]), d = F3(rd[3 * i], rd[3 * i + 1], rd[3 * i + 2]);
+    float t, u, v;
+    int id = bvh_closest(b, o, d, t, u, v);
+    tri_id[i] = id; tuv[3 * i] = t; tuv[3 * i + 1] = u; tuv[3 * i + 2] = v;
+}
+
+inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+}  // namespace
+
+extern "C" {
+
+int mcs_ctx_create(mcs_ctx **out)
+{
+    MCS_REQUIRE(out != nullptr, "mcs_ctx_create: null output pointer");
+    int dev = 0;
+    MCS_CUDA(cudaGetDevice(&dev));
+    mcs_ctx *c = new mcs_ctx();
+    c->device = dev;
+    *out = c;
+    return 0;
+}
+
+int mcs_ctx_destroy(mcs_ctx *c)
+{
+    if (!c) return 0;
+    DevBuf *bufs[] = {&c->bounds, &c->tlo, &c->thi, &c->keys, &c->keys_alt, &c->vals, &c->vals_alt, &c->left, &c->right, &c->parent,
+                      &c->lo, &c->hi, &c->flags, &c->sort_tmp, &c->nodes, &c->tris, &c->lcg_skip, &c->light_grad4};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    delete c;
+    return 0;
+}
+
+int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris, int32_t T, uint32_t rebuild, mcs_stream stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    MCS_REQUIRE(c != nullptr, "mcs_bvh_build: null context");
+    MCS_REQUIRE(verts && tris, "mcs_bvh_build: null geometry pointer");
+    // ops.py:131-132: "Got empty training triangle mesh (unrecoverable discontinuity)"
+    MCS_REQUIRE(T > 0 && V > 0, "Got empty training triangle mesh (unrecoverable discontinuity)");
+    MCS_REQUIRE(rebuild != 0 || c->T == T, "mcs_bvh_build: refit (rebuild=0) needs an existing structure with the same triangle count (have %d, got %d)", c->T, T);
+    const size_t nT = (size_t)T, nN = 2 * nT - 1;
+    if (int e = mcs_buf_reserve(c->bounds, 12 * sizeof(uint32_t), s)) return e;
+    if (int e = mcs_buf_reserve(c->tlo, nT * 3 * sizeof(float), s)) return e;
+    if (int e = mcs_buf_reserve(c->thi, nT * 3 * sizeof(float), s)) return e;
+    if (int e = mcs_buf_reserve(c->keys, nT * sizeof(uint32_t), s)) return e;
+    if (int e = mcs_buf_reserve(c->keys_alt, nT * sizeof(uint32_t), s)) return e;
+    if (int e = mcs_buf_reserve(c->vals, nT * sizeof(int32_t), s)) return e;
+    if (int e = mcs_buf_reserve(c->vals_alt, nT * sizeof(int32_t), s)) return e;
+    if (int e = mcs_buf_reserve(c->left, nT * sizeof(int32_t), s)) return e;
+    if (int e = mcs_buf_reserve(c->right, nT * sizeof(int32_t), s)) return e;
+    if (int e = mcs_buf_reserve(c->parent, nN * sizeof(int32_t), s)) return e;
+    if (int e = mcs_buf_reserve(c->lo, nN * 3 * sizeof(float), s)) return e;
+    if (int e = mcs_buf_reserve(c->hi, nN * 3 * sizeof(float), s)) return e;
+    if (int e = mcs_buf_reserve(c->flags, nT * sizeof(int), s)) return e;
+    if (int e = mcs_buf_reserve(c->nodes, nT * 4 * sizeof(float4), s)) return e;
+    if (int e = mcs_buf_reserve(c->tris, nT * 3 * sizeof(float4), s)) return e;
+
+    uint32_t *bounds = (uint32_t *)c->bounds.p;
+    float *tlo = (float *)c->tlo.p, *thi = (float *)c->thi.p;
+    k_bounds_init<<<1, 32, 0, s>>>(bounds);
+    k_tri_bounds<<<nblk(T, 256), 256, 0, s>>>(verts, tris, T, tlo, thi, bounds);
+    MCS_LAUNCH_CHECK();
+    if (rebuild) {
+        k_morton<<<nblk(T, 256), 256, 0, s>>>(tlo, thi, T, bounds, (uint32_t *)c->keys.p, (int32_t *)c->vals.p);
+        MCS_LAUNCH_CHECK();
+        size_t tmp_bytes = 0;
+        MCS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)c->keys.p, (uint32_t *)c->keys_alt.p,
+                                                 (const int32_t *)c->vals.p, (int32_t *)c->vals_alt.p, T, 0, 30, s));
+        if (int e = mcs_buf_reserve(c->sort_tmp, tmp_bytes, s)) return e;
+        MCS_CUDA(cub::DeviceRadixSort::SortPairs(c->sort_tmp.p, tmp_bytes, (const uint32_t *)c->keys.p, (uint32_t *)c->keys_alt.p,
+                                                 (const int32_t *)c->vals.p, (int32_t *)c->vals_alt.p, T, 0, 30, s));
+        if (T > 1) {
+            k_karras<<<nblk(T - 1, 256), 256, 0, s>>>((const uint32_t *)c->keys_alt.p, T, (int32_t *)c->left.p, (int32_t *)c->right.p, (int32_t *)c->parent.p);
+            MCS_LAUNCH_CHECK();
+        }
+    }
+    MCS_CUDA(cudaMemsetAsync(c->flags.p, 0, nT * sizeof(int), s));
+    k_leaves_refit<<<nblk(T, 256), 256, 0, s>>>(verts, tris, T, tlo, thi, (const int32_t *)c->vals_alt.p, bounds, (const int32_t *)c->left.p,
+                                                (const int32_t *)c->right.p, (const int32_t *)c->parent.p, (float *)c->lo.p, (float *)c->hi.p,
+                                                (int *)c->flags.p, (float4 *)c->tris.p);
+    MCS_LAUNCH_CHECK();
+    k_emit_nodes<<<nblk(T > 1 ? T - 1 : 1, 256), 256, 0, s>>>(T, (const int32_t *)c->left.p, (const int32_t *)c->right.p, (const float *)c->lo.p,
+                                                              (const float *)c->hi.p, (float4 *)c->nodes.p);
+    MCS_LAUNCH_CHECK();
+    c->T = T; c->V = V;
+    return 0;
+}
+
+int mcs_bvh_export(mcs_ctx *c, uint32_t *morton, int32_t *prim, int32_t *left, int32_t *right, float *lo, float *hi, mcs_stream stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    MCS_REQUIRE(c && c->T > 0, "mcs_bvh_export: no acceleration structure built");
+    size_t T = (size_t)c->T;
+    MCS_CUDA(cudaMemcpyAsync(morton, c->keys_alt.p, T * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    MCS_CUDA(cudaMemcpyAsync(prim, c->vals_alt.p, T * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    if (T > 1) {
+        MCS_CUDA(cudaMemcpyAsync(left, c->left.p, (T - 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+        MCS_CUDA(cudaMemcpyAsync(right, c->right.p, (T - 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    }
+    MCS_CUDA(cudaMemcpyAsync(lo, c->lo.p, (2 * T - 1) * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    MCS_CUDA(cudaMemcpyAsync(hi, c->hi.p, (2 * T - 1) * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+int mcs_trace_visibility(mcs_ctx *c, const float *ro, const float *rd, int64_t n, uint8_t *vis, mcs_stream stream)
+{
+    MCS_REQUIRE(c && c->T > 0, "mcs_trace_visibility: no acceleration structure built (call mcs_bvh_build first)");
+    MCS_REQUIRE(n >= 0 && (n == 0 || (ro && rd && vis)), "mcs_trace_visibility: bad arguments");
+    if (n == 0) return 0;
+    BvhView b{(const float4 *)c->nodes.p, (const float4 *)c->tris.p};
+    k_visibility<<<nblk(n, 128), 128, 0, (cudaStream_t)stream>>>(b, ro, rd, n, vis);
+    MCS_LAUNCH_CHECK();
+    return 0;
+}
+
+int mcs_trace_closest(mcs_ctx *c, const float *ro, const float *rd, int64_t n, int32_t *tri_id, float *tuv, mcs_stream stream)
+{
+    MCS_REQUIRE(c && c->T > 0, "mcs_trace_closest: no acceleration structure built (call mcs_bvh_build first)");
+    MCS_REQUIRE(n >= 0 && (n == 0 || (ro && rd && tri_id && tuv)), "mcs_trace_closest: bad arguments");
+    if (n == 0) return 0;
+    BvhView b{(const float4 *)c->nodes.p, (const float4 *)c->tris.p};
+    k_closest<<<nblk(n, 128), 128, 0, (cudaStream_t)stream>>>(b, ro, rd, n, tri_id, tuv);
+    MCS_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,35 @@
+// ctx.h -- the opaque per-scene context behind mcs_ctx (replaces OptiXState,
+// render/optixutils/c_src/optix_wrapper.h:17-37): owns the acceleration structure and all build
+// workspace.  Buffers grow by doubling and are stream-ordered (cudaMallocAsync), so the per-iteration
+// rebuild (geometry/dlmesh.py:50, dmtet.py:202) never synchronises the host or touches the allocator
+// in steady state.
+#pragma once
+#include "common.cuh"
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct mcs_ctx {
+    int device = 0;
+    int T = 0, V = 0;            // triangles / vertices of the current structure (0 = none built)
+    // ---- binary LBVH (canonical, exported for parity tests) ----
+    DevBuf bounds;               // 12 x uint32 order-preserving encoded: cmin, cmax, smin, smax
+    DevBuf tlo, thi;             // [T][3] raw triangle boxes
+    DevBuf keys, keys_alt;       // [T] Morton codes (unsorted / sorted)
+    DevBuf vals, vals_alt;       // [T] triangle ids   (unsorted / sorted)
+    DevBuf left, right, parent;  // [T-1],[T-1],[2T-1]
+    DevBuf lo, hi;               // [2T-1][3] padded node boxes
+    DevBuf flags;                // [T-1] refit arrival counters
+    DevBuf sort_tmp;
+    // ---- traversal layout ----
+    DevBuf nodes;                // [max(T-1,1)] x 4 float4 (two child boxes + child codes)
+    DevBuf tris;                 // [T] x 3 float4 in SORTED order: (v0, orig id), (e1, -), (e2, -)
+    // ---- env_shade support ----
+    DevBuf lcg_skip;             // [5*N*N+3] x uint2 (mul, add) LCG jump-ahead table for n_samples_x = skip_N
+    int skip_N = 0;
+    DevBuf light_grad4;          // scratch
+};
+
+int mcs_buf_reserve(DevBuf &b, size_t bytes, cudaStream_t s);

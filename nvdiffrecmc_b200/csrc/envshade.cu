@@ -1,0 +1,611 @@
+// envshade.cu -- fused environment-light MIS sampling + shadow rays + PBR BSDF, forward and backward.
+//
+// Replaces the OptiX raygen program __raygen__rg / process_sample / shadow_test
+// (render/optixutils/c_src/envsampling/kernel.cu:101-118, 403-542) and its launchers env_shade_fwd /
+// env_shade_bwd (render/optixutils/c_src/torch_bindings.cpp:123-272).
+//
+// B200 mapping (no RT cores, 148 SMs):
+//   * ONE WARP PER PIXEL, ONE LANE PER SAMPLE.  The reference runs one thread per pixel and loops
+//     2*N^2 samples serially; here the 2*N^2 (stratum, sample-type) items of a pixel are spread over
+//     the 32 lanes (items [0,N^2) are light samples, [N^2,2N^2) BSDF samples, so a 32-item round is
+//     type-uniform whenever N^2 is a multiple of 32).  All rays of a warp share their origin, which
+//     keeps the top of the BVH walk coherent, and the per-pixel G-buffer record is loaded once per
+//     warp with broadcast loads.  Per-lane partial sums are combined with warp shuffles and written
+//     once: no G-buffer round trip, no atomics except the env-map gradient.
+//   * The reference's per-pixel PCG stream is sequential (5 uniforms per stratum); lanes jump to their
+//     position with a precomputed LCG skip table (state' = state*mul[k] + add[k]), so the random
+//     numbers are bit-identical to the reference stream (kernel.cu:30-45, 504-524).
+//   * Persistent warps: grid = #SMs x resident CTAs, each warp claims 32-pixel chunks from a global
+//     counter (coverage is ~35 %: masked chunks cost one coalesced load + ballot).
+//   * Rays whose unshadowed contribution is exactly zero (n.wi <= 0: Lambert and the GGX lobe both
+//     vanish, and so do all their adjoints) are not traced; this is output-preserving and removes
+//     about half of the light-sampled rays.
+//   * Sampling decisions use exact.cuh arithmetic (bit-identical texel / direction / lobe choice vs
+//     the oracle); BSDF evaluation, pdfs and adjoints use fast FMA math (bsdf.cuh).
+//   * Backward replays the same random stream, evaluates the adjoint BSDF only for visible rays,
+//     reduces the per-pixel gradients in registers/shuffles (single writer per pixel like the
+//     reference's `+=`, kernel.cu:442-456) and scatters the env-map gradient with float atomics
+//     (kernel.cu:203-211), skipping zero contributions.
+#include "bsdf.cuh"
+#include "bvh_traverse.cuh"
+#include "ctx.h"
+#include "exact.cuh"
+#include <vector>
+
+namespace {
+
+constexpr int WARPS_PER_CTA = 8;
+constexpr float MIN_ROUGHNESS = 0.08f;     // kernel.cu:17
+
+struct EnvParams {
+    TView mask, ro, pos, nrm, view, kd, ks;
+    const float *light; int l_s1, l_s2, l_s3;      // [Hl,Wl,3] strides
+    const float *pdf; int p_s1, p_s2;
+    const float *rows; int r_s;
+    const float *cols; int c_s1, c_s2;
+    const int32_t *perms; int pm_s1, pm_s3; uint32_t n_perms;
+    int Hl, Wl, m_rows, m_cols;
+    int B, H, W;
+    int N, S;
+    uint32_t bsdf, seed;
+    int batch_offset;
+    float shadow_scale;
+    BvhView bvh;
+    const uint2 *skip;
+    unsigned int *chunk_counter;
+    // fwd
+    float *diff, *spec;
+    int32_t *rec_texel; uint8_t *rec_vis;
+    // bwd
+    TView diff_grad, spec_grad;
+    float *pos_grad, *nrm_grad, *kd_grad, *ks_grad, *light_grad;
+};
+
+// kernel.cu:30-35
+__device__ __forceinline__ uint32_t rand_pcg(uint32_t &s)
+{
+    uint32_t word = ((s >> ((s >> 28u) + 4u)) ^ s) * 277803737u;
+    s = s * 747796405u + 2891336453u;
+    return (word >> 22u) ^ word;
+}
+__device__ __forceinline__ xf uniform_pcg(uint32_t &s)
+{
+    return xf((float)(rand_pcg(s) & 0xFFFFFFu) * (1.0f / 16777216.0f));      // exact: division by 2^24
+}
+
+// kernel.cu:140-169; cdf element i at cdf[i*stride]
+__device__ __forceinline__ xf sample_cdf(const float *__restrict__ cdf, int stride, int size, int m, xf x, uint32_t &idx)
+{
+    x = xmin(x, xf(0.99999994f));
+    uint32_t lo = 0, hi = (uint32_t)size - 1;
+    for (int i = 0; i < m; ++i) {
+        uint32_t mid = (lo + hi) >> 1;
+        float c = __ldg(cdf + (size_t)mid * stride);
+        lo = x.v >= c ? mid : lo;
+        hi = x.v < c ? mid : hi;
+    }
+    idx = hi;
+    xf pdf, sample;
+    if (idx == 0) { pdf = xf(__ldg(cdf)); sample = x; }
+    else {
+        xf d0 = xf(__ldg(cdf + (size_t)idx * stride)), d1 = xf(__ldg(cdf + (size_t)(idx - 1) * stride));
+        pdf = d0 - d1; sample = x - d1;
+    }
+    return xmin(sample / pdf, xf(0.99999994f));
+}
+
+struct Texel { int x, y; float sin_theta_arg; };
+
+// kernel.cu:124-129 + 177-178: direction -> lat-long coordinate -> nearest texel (decision path)
+__device__ __forceinline__ void dir_to_texel(const EnvParams &p, xf3 dir, int &tx, int &ty, float &cy)
+{
+    xf a = det_atan2(dir.x, -dir.z);
+    float u = __double2float_rn(xd_add(xd_div((double)a.v, 2.0 * XD_PI), 0.5));
+    xf ac = det_acos(xclamp(dir.y, xf(-1.0f), xf(1.0f)));
+    float v = __double2float_rn(xd_div((double)ac.v, XD_PI));
+    tx = min(max(__float2int_rz(__fmul_rn(u, (float)p.Wl)), 0), p.Wl - 1);
+    ty = min(max(__float2int_rz(__fmul_rn(v, (float)p.Hl)), 0), p.Hl - 1);
+    cy = v;
+}
+// kernel.cu:131-138
+__device__ __forceinline__ xf3 tc_to_dir(xf ux, xf uy)
+{
+    xf sphi, cphi, sth, cth;
+    det_sincos(xf(__double2float_rn(xd_mul((double)(ux * xf(2.0f) - xf(1.0f)).v, XD_PI))), sphi, cphi);
+    det_sincos(xf(__double2float_rn(xd_mul((double)uy.v, XD_PI))), sth, cth);
+    return X3(sth * sphi, cth, -sth * cphi);
+}
+// kernel.cu:171-182 (value only; the texel comes from dir_to_texel)
+__device__ __forceinline__ float light_pdf_value(const EnvParams &p, int tx, int ty, float cy)
+{
+    float w = (float)(p.Hl * p.Wl) / (2.0f * MCS_PI * MCS_PI * fmaxf(sinpif(cy), 0.0001f));
+    return __ldg(p.pdf + (size_t)ty * p.p_s1 + (size_t)tx * p.p_s2) * w;
+}
+
+// kernel.cu:217-237
+__device__ __forceinline__ float eval_ndf_ggx(float alpha, float c)
+{
+    float a2 = alpha * alpha;
+    float d = (c * a2 - c) * c + 1.0f;
+    return a2 / (d * d * MCS_PI);
+}
+__device__ __forceinline__ float eval_g1_ggx(float alphaSqr, float c)
+{
+    if (c <= 0.0f) return 0.0f;
+    float c2 = c * c;
+    float t2 = fmaxf(1.0f - c2, 0.0f) / c2;
+    return 2.0f / (1.0f + sqrtf(1.0f + alphaSqr * t2));
+}
+
+// Per-pixel shading frame and lobe probabilities (kernel.cu:490-502), shared by all items of a pixel
+struct PixelFrame {
+    xf3 N;            // gb_normal as given
+    xf3 W, U, V;      // normalised normal + orthonormal basis
+    xf3 wo;           // view direction
+    xf3 wo_l_raw;     // tolocal(wo)      (ggx_pdf uses it un-normalised, kernel.cu:310)
+    xf3 wo_l;         // normalised       (albedo / ggx_sample, kernel.cu:87,275)
+    xf alpha;
+    xf pDiffuse, pSpecular;
+    xf NdotV;
+};
+
+__device__ __forceinline__ xf3 x_tolocal(xf3 a, const PixelFrame &f) { return X3(xdot(a, f.U), xdot(a, f.V), xdot(a, f.W)); }
+__device__ __forceinline__ xf3 x_toworld(xf3 a, const PixelFrame &f) { return f.U * a.x + f.V * a.y + f.W * a.z; }
+
+// kernel.cu:301-323 (value path)
+__device__ __forceinline__ float ggx_pdf_value(const PixelFrame &f, f3 wi)
+{
+    f3 wo_l = toF3(f.wo_l_raw);
+    f3 wi_l = F3(dot(wi, toF3(f.U)), dot(wi, toF3(f.V)), dot(wi, toF3(f.W)));
+    float pdf = 0.0f;
+    if (wo_l.z > 0.0f && wi_l.z > 0.0f) {
+        f3 m = safe_normalize(wi_l + wo_l);
+        float woDotH = dot(m, wo_l);
+        float alpha = f.alpha.v;
+        float D = eval_ndf_ggx(alpha, m.z);
+        float G1 = eval_g1_ggx(alpha * alpha, wo_l.z);
+        pdf = G1 * D * fmaxf(0.0f, woDotH) / wo_l.z;
+        pdf /= (4.0f * woDotH);
+    }
+    return pdf;
+}
+__device__ __forceinline__ void update_pdf(float &pdf, float opdf, float b) { if (b > 0.000001f) pdf += opdf * b; }   // kernel.cu:325-332
+
+// kernel.cu:374-397
+__device__ __forceinline__ float bsdf_pdf_value(const PixelFrame &f, xf3 wi)
+{
+    xf NdotL = xdot(f.N, wi);
+    if (xmin(f.NdotV, NdotL).v < 1e-6f) return 1.0f;
+    float pdf = 0.0f;
+    float pD = f.pDiffuse.v;
+    if (pD > 0.0f) update_pdf(pdf, fmaxf(NdotL.v, 0.0f) * MCS_INV_PI, pD);
+    if (f.pSpecular.v > 0.0f) update_pdf(pdf, ggx_pdf_value(f, toF3(wi)), 1.0f - pD);
+    return pdf;
+}
+
+// kernel.cu:334-372 (direction on the exact path, pdf on the value path)
+__device__ __forceinline__ xf3 bsdf_sample(const PixelFrame &f, xf sx, xf sy, xf sz, float &pdf)
+{
+    pdf = 0.0f;
+    const float pD = f.pDiffuse.v;
+    xf3 wi;
+    if (sz < f.pDiffuse) {
+        if (pD < 0.0001f) { pdf = 1.0f; return f.N; }
+        // cosine_sample, kernel.cu:57-79
+        xf phi = xf(__double2float_rn(xd_mul(2.0 * XD_PI, (double)sx.v)));
+        xf ct = xsqrt(sy);
+        xf st = xf(__double2float_rn(__dsqrt_rn(__dsub_rn(1.0, (double)sy.v))));
+        xf sp, cp;
+        det_sincos(phi, sp, cp);
+        xf3 vec = f.U * (cp * st) + f.V * (sp * st) + f.W * ct;
+        wi = xnormalize(vec);
+        pdf = fmaxf(0.000001f, ct.v * MCS_INV_PI) * pD;
+        if (f.pSpecular.v > 0.0f) update_pdf(pdf, ggx_pdf_value(f, toF3(wi)), 1.0f - pD);
+    } else {
+        // ggx_sample / sampleGGX_VNDF, kernel.cu:241-291
+        if (!(f.wo_l.z.v > 0.0f)) { pdf = 0.0f; wi = X3(xf(0.0f), xf(0.0f), xf(0.0f)); }
+        else {
+            const xf alpha = f.alpha;
+            xf3 Vh = xnormalize(X3(alpha * f.wo_l.x, alpha * f.wo_l.y, f.wo_l.z));
+            xf3 T1 = (Vh.z.v < 0.9999f) ? xnormalize(xcross(X3(xf(0.0f), xf(0.0f), xf(1.0f)), Vh)) : X3(xf(1.0f), xf(0.0f), xf(0.0f));
+            xf3 T2 = xcross(Vh, T1);
+            xf r = xsqrt(sx);
+            xf phi = (xf(2.0f) * xf(MCS_PI)) * sy;
+            xf sp, cp;
+            det_sincos(phi, sp, cp);
+            xf t1 = r * cp, t2 = r * sp;
+            xf s = xf(0.5f) * (xf(1.0f) + Vh.z);
+            t2 = (xf(1.0f) - s) * xsqrt(xf(1.0f) - t1 * t1) + s * t2;
+            xf3 Nh = T1 * t1 + T2 * t2 + Vh * xsqrt(xmax(xf(0.0f), xf(1.0f) - t1 * t1 - t2 * t2));
+            xf3 h = xnormalize(X3(alpha * Nh.x, alpha * Nh.y, xmax(xf(0.0f), Nh.z)));
+            xf woDotH = xdot(f.wo_l, h);
+            xf3 wi_l = h * woDotH * xf(2.0f) - f.wo_l;
+            wi = xnormalize(x_toworld(wi_l, f));
+            // evalPdfGGX_VNDF, kernel.cu:232-237, then the reflection Jacobian (:287)
+            float a = alpha.v, woz = f.wo_l.z.v;
+            float G1 = eval_g1_ggx(a * a, woz);
+            float D = eval_ndf_ggx(a, h.z.v);
+            pdf = G1 * D * fmaxf(0.0f, woDotH.v) / woz;
+            pdf /= (4.0f * woDotH.v);
+        }
+        pdf *= 1.0f - pD;
+        if (pD > 0.0f) update_pdf(pdf, fmaxf(xdot(f.N, wi).v, 0.0f) * MCS_INV_PI, pD);
+    }
+    return wi;
+}
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// MODE 0: forward, 1: backward, 2: forward + per-ray records
+template <int MODE>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) env_shade_kernel(const EnvParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t npix = (int64_t)p.B * p.H * p.W;
+    const unsigned int nchunks = (unsigned int)((npix + 31) / 32);
+    const int S = p.S, items = 2 * S;
+    const xf strata_frac = xf(1.0f) / xf((float)(unsigned)p.N);
+    const float sample_frac = (xf(1.0f) / xf((float)(unsigned)(p.N * p.N))).v;
+    const bool diffuse_only = (p.bsdf == 1u || p.bsdf == 2u);
+    const bool trace_needed = p.shadow_scale != 0.0f;
+
+    while (true) {
+        unsigned int chunk = 0;
+        if (lane == 0) chunk = atomicAdd(p.chunk_counter, 1u);
+        chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
+        if (chunk >= nchunks) break;
+
+        const int64_t mypix = (int64_t)chunk * 32 + lane;
+        int mz = 0, my = 0, mx = 0;
+        bool mine = mypix < npix;
+        float mval = 0.0f;
+        if (mine) {
+            mx = (int)(mypix % p.W); int64_t t = mypix / p.W; my = (int)(t % p.H); mz = (int)(t / p.H);
+            mval = p.mask.ld1(mz, my, mx);
+        }
+        const unsigned active = __ballot_sync(0xFFFFFFFFu, mine && mval > 0.0f);
+        if (mine && !(mval > 0.0f)) {
+            // masked pixel: outputs are zero (the reference returns early on zero-initialised tensors, kernel.cu:478)
+            if (MODE != 1) {
+                float *d = p.diff + mypix * 3, *s = p.spec + mypix * 3;
+                d[0] = d[1] = d[2] = 0.0f; s[0] = s[1] = s[2] = 0.0f;
+            } else {
+                float *a = p.pos_grad + mypix * 3, *b = p.nrm_grad + mypix * 3, *c = p.kd_grad + mypix * 3, *d = p.ks_grad + mypix * 3;
+                a[0] = a[1] = a[2] = 0.0f; b[0] = b[1] = b[2] = 0.0f; c[0] = c[1] = c[2] = 0.0f; d[0] = d[1] = d[2] = 0.0f;
+            }
+        }
+
+        unsigned rem = active;
+        while (rem) {
+            const int src = __ffs(rem) - 1;
+            rem &= rem - 1;
+            const int64_t pix = (int64_t)chunk * 32 + src;
+            const int ix = (int)(pix % p.W);
+            const int64_t tt = pix / p.W;
+            const int iy = (int)(tt % p.H), iz = (int)(tt / p.H);
+
+            // ---- per-pixel record (broadcast loads) and shading frame ----
+            const f3 ro = p.ro.ld3(iz, iy, ix);
+            const f3 pos = p.pos.ld3(iz, iy, ix);
+            const f3 nrm = p.nrm.ld3(iz, iy, ix);
+            const f3 view = p.view.ld3(iz, iy, ix);
+            const f3 kd = p.kd.ld3(iz, iy, ix);
+            const f3 ks = p.ks.ld3(iz, iy, ix);
+
+            PixelFrame f;
+            f.N = X3(nrm);
+            f.alpha = xf(ks.y) * xf(ks.y);
+            f.wo = xnormalize(X3(view) - X3(pos));
+            {
+                xf metallic = xf(ks.z);
+                xf3 base = X3(kd);
+                xf om = xf(1.0f) - metallic;
+                xf3 specColor = X3(xf(0.04f) * om + base.x * metallic, xf(0.04f) * om + base.y * metallic, xf(0.04f) * om + base.z * metallic);
+                xf lum = base.x * xf(0.2126f) + base.y * xf(0.7152f) + base.z * xf(0.0722f);
+                xf diffuseWeight = om * lum;
+                // albedo(), kernel.cu:81-94
+                f.W = xnormalize(f.N);
+                xONB(f.W, f.U, f.V);
+                f.wo_l_raw = x_tolocal(f.wo, f);
+                f.wo_l = xnormalize(f.wo_l_raw);
+                xf specularWeight = xf(0.0f);
+                if (f.wo_l.z.v > 0.0f) {
+                    xf c = xclamp(f.wo_l.z, xf(1e-4f), xf(1.0f) - xf(1e-4f));
+                    xf o = xf(1.0f) - c;
+                    xf o2 = o * o;
+                    xf scale = (o2 * o2) * o;
+                    xf os = xf(1.0f) - scale;
+                    xf3 F = X3(specColor.x * os + scale, specColor.y * os + scale, specColor.z * os + scale);
+                    specularWeight = F.x * xf(0.2126f) + F.y * xf(0.7152f) + F.z * xf(0.0722f);
+                }
+                xf sumw = diffuseWeight + specularWeight;
+                f.pDiffuse = sumw.v > 0.0f ? diffuseWeight / sumw : xf(1.0f);
+                f.pSpecular = xf(1.0f) - f.pDiffuse;
+                f.NdotV = xdot(f.N, f.wo);
+            }
+            const f3 wo_f = toF3(f.wo);
+
+            f3 dgrad = F3(0.0f), sgrad = F3(0.0f);
+            if (MODE == 1) { dgrad = p.diff_grad.ld3(iz, iy, ix); sgrad = p.spec_grad.ld3(iz, iy, ix); }
+
+            // RNG, kernel.cu:504-505
+            uint32_t s_seed = p.seed, s_pix = (uint32_t)(((iz + p.batch_offset) * p.H + iy) * p.W + ix);
+            uint32_t rng = rand_pcg(s_seed) ^ rand_pcg(s_pix);
+            const uint32_t lightIdx = rand_pcg(rng) % p.n_perms;
+            const uint32_t bsdfIdx = rand_pcg(rng) % p.n_perms;
+            const uint32_t rng2 = rng;
+
+            f3 accD = F3(0.0f), accS = F3(0.0f);                       // fwd accumulators
+            f3 g_kd = F3(0.0f), g_ks = F3(0.0f), g_nrm = F3(0.0f), g_wo = F3(0.0f);   // bwd accumulators
+
+            for (int base = 0; base < items; base += 32) {
+                const int w = base + lane;
+                const bool valid = w < items;
+                const bool is_bsdf = w >= S;
+                const int i = is_bsdf ? w - S : w;
+
+                xf3 dir = X3(xf(0.0f), xf(0.0f), xf(1.0f));
+                float pdf_sum = 1.0f;
+                int tx = 0, ty = 0;
+                if (valid) {
+                    const uint2 sk = __ldg(p.skip + 5 * i + (is_bsdf ? 2 : 0));
+                    uint32_t st = rng2 * sk.x + sk.y;
+                    const uint32_t row = is_bsdf ? bsdfIdx : lightIdx;
+                    const uint32_t perm = (uint32_t)__ldg(p.perms + (size_t)row * p.pm_s1 + (size_t)i * p.pm_s3);
+                    const xf sx = (xf((float)(perm % (uint32_t)p.N)) + uniform_pcg(st)) * strata_frac;
+                    const xf sy = (xf((float)(perm / (uint32_t)p.N)) + uniform_pcg(st)) * strata_frac;
+                    float cy;
+                    if (!is_bsdf) {
+                        // lightSample, kernel.cu:184-193
+                        uint32_t cyi, cxi;
+                        xf ry = sample_cdf(p.rows, p.r_s, p.Hl, p.m_rows, sy, cyi);
+                        xf rx = sample_cdf(p.cols + (size_t)cyi * p.c_s1, p.c_s2, p.Wl, p.m_cols, sx, cxi);
+                        dir = tc_to_dir((xf((float)cxi) + rx) / xf((float)p.Wl), (xf((float)cyi) + ry) / xf((float)p.Hl));
+                        dir_to_texel(p, dir, tx, ty, cy);
+                        const float pdf_light = light_pdf_value(p, tx, ty, cy);
+                        const float pdf_b = bsdf_pdf_value(f, dir);
+                        pdf_sum = pdf_light + pdf_b;
+                    } else {
+                        const xf sz = uniform_pcg(st);
+                        float pdf_b;
+                        dir = bsdf_sample(f, sx, sy, sz, pdf_b);
+                        dir_to_texel(p, dir, tx, ty, cy);
+                        pdf_sum = light_pdf_value(p, tx, ty, cy) + pdf_b;
+                    }
+                }
+
+                // process_sample, kernel.cu:403-461
+                const f3 wi = toF3(dir);
+                f3 light_col = F3(0.0f);
+                float diffv = 0.0f; f3 specv = F3(0.0f);
+                bool contributes = false;
+                if (valid) {
+                    const float *lp = p.light + (size_t)ty * p.l_s1 + (size_t)tx * p.l_s2;
+                    light_col = F3(__ldg(lp), __ldg(lp + p.l_s3), __ldg(lp + 2 * p.l_s3));
+                    if (diffuse_only) diffv = fwd_lambert(nrm, wi);
+                    else ox_fwd_pbr_bsdf(kd, ks, wo_f, nrm, wi, MIN_ROUGHNESS, diffv, specv);
+                    contributes = (diffv != 0.0f) || (specv.x != 0.0f) || (specv.y != 0.0f) || (specv.z != 0.0f);
+                }
+                const float mis = 1.0f / fmaxf(pdf_sum, 0.0001f);
+
+                bool visible = true;
+                const bool traced = valid && contributes && trace_needed;
+                if (traced) visible = !bvh_occluded(p.bvh, ro, wi);
+                const float Vv = (visible ? 1.0f : 0.0f) * p.shadow_scale + (1.0f - p.shadow_scale);
+
+                if (MODE == 2 && valid) {
+                    const size_t rec = (size_t)pix * items + (size_t)(2 * i + (is_bsdf ? 1 : 0));
+                    p.rec_texel[rec] = (ty << 16) | tx;
+                    p.rec_vis[rec] = traced ? (visible ? 1 : 0) : 2;
+                }
+
+                const float wgt = Vv * mis * sample_frac;
+                if (MODE != 1) {
+                    if (valid && contributes) {
+                        accD += light_col * (diffv * wgt);
+                        accS += specv * light_col * wgt;
+                    }
+                } else if (valid && contributes && wgt != 0.0f) {
+                    // light gradient, kernel.cu:424-425 / 203-211
+                    const f3 lg = (dgrad * diffv + sgrad * specv) * wgt;
+                    float *gp = p.light_grad + ((size_t)ty * p.Wl + tx) * 3;
+                    if (lg.x != 0.0f) atomicAdd(gp, lg.x);
+                    if (lg.y != 0.0f) atomicAdd(gp + 1, lg.y);
+                    if (lg.z != 0.0f) atomicAdd(gp + 2, lg.z);
+                    const f3 dD = dgrad * light_col * wgt, dS = sgrad * light_col * wgt;
+                    if (diffuse_only) {
+                        f3 wi_grad = F3(0.0f);
+                        bwd_lambert(nrm, wi, g_nrm, wi_grad, sum(dD));
+                    } else {
+                        ox_bwd_pbr_bsdf(kd, ks, wo_f, nrm, wi, MIN_ROUGHNESS, g_kd, g_ks, g_wo, g_nrm, sum(dD), dS);
+                    }
+                }
+            }
+
+            // ---- warp reduction, single writer per pixel ----
+            if (MODE != 1) {
+                float r0 = warp_sum(accD.x), r1 = warp_sum(accD.y), r2 = warp_sum(accD.z);
+                float r3 = warp_sum(accS.x), r4 = warp_sum(accS.y), r5 = warp_sum(accS.z);
+                if (lane == 0) {
+                    float *d = p.diff + pix * 3, *s = p.spec + pix * 3;
+                    d[0] = r0; d[1] = r1; d[2] = r2; s[0] = r3; s[1] = r4; s[2] = r5;
+                }
+            } else {
+                f3 t_kd = F3(warp_sum(g_kd.x), warp_sum(g_kd.y), warp_sum(g_kd.z));
+                f3 t_ks = F3(warp_sum(g_ks.x), warp_sum(g_ks.y), warp_sum(g_ks.z));
+                f3 t_nrm = F3(warp_sum(g_nrm.x), warp_sum(g_nrm.y), warp_sum(g_nrm.z));
+                f3 t_wo = F3(warp_sum(g_wo.x), warp_sum(g_wo.y), warp_sum(g_wo.z));
+                if (lane == 0) {
+                    // wo = normalize(view_pos - pos): d_pos = -J^T d_wo (bsdf.h:270-274; d_view_pos is dropped, ops.py:105)
+                    f3 d__wo = F3(0.0f);
+                    bwd_safe_normalize(view - pos, d__wo, t_wo);
+                    float *a = p.pos_grad + pix * 3, *b = p.nrm_grad + pix * 3, *c = p.kd_grad + pix * 3, *d = p.ks_grad + pix * 3;
+                    a[0] = -d__wo.x; a[1] = -d__wo.y; a[2] = -d__wo.z;
+                    b[0] = t_nrm.x; b[1] = t_nrm.y; b[2] = t_nrm.z;
+                    c[0] = t_kd.x; c[1] = t_kd.y; c[2] = t_kd.z;
+                    d[0] = t_ks.x; d[1] = t_ks.y; d[2] = t_ks.z;
+                }
+            }
+        }
+    }
+}
+
+static int ensure_skip_table(mcs_ctx *c, int N, cudaStream_t s)
+{
+    if (c->skip_N == N && c->lcg_skip.p) return 0;
+    const int n = 5 * N * N + 3;
+    std::vector<uint2> h((size_t)n);
+    uint32_t m = 1u, a = 0u;
+    for (int k = 0; k < n; ++k) {
+        h[(size_t)k] = make_uint2(m, a);
+        a = a * 747796405u + 2891336453u;       // one more LCG step (kernel.cu:33)
+        m = m * 747796405u;
+    }
+    if (int e = mcs_buf_reserve(c->lcg_skip, sizeof(uint2) * (size_t)n + 16, s)) return e;
+    MCS_CUDA(cudaMemcpyAsync(c->lcg_skip.p, h.data(), sizeof(uint2) * (size_t)n, cudaMemcpyHostToDevice, s));
+    MCS_CUDA(cudaStreamSynchronize(s));        // one-off (table is cached per n_samples_x); keeps `h` alive
+    c->skip_N = N;
+    return 0;
+}
+
+static int cdf_iters(int size)
+{
+    // kernel.cu:147  m = int(ceil(log2((float)_max))) + 1
+    unsigned int mx = (unsigned int)size - 1;
+    return (int)ceil(log2((double)(float)mx)) + 1;
+}
+
+static int fill_params(mcs_ctx *ctx, EnvParams &p,
+                       const mcs_tensor *mask, const mcs_tensor *ro, const mcs_tensor *gb_pos, const mcs_tensor *gb_normal,
+                       const mcs_tensor *gb_view_pos, const mcs_tensor *gb_kd, const mcs_tensor *gb_ks,
+                       const mcs_tensor *light, const mcs_tensor *pdf, const mcs_tensor *rows, const mcs_tensor *cols,
+                       const mcs_tensor *perms, uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
+                       cudaStream_t s)
+{
+    MCS_REQUIRE(ctx != nullptr, "env_shade: null context");
+    MCS_REQUIRE(ctx->T > 0, "env_shade: no acceleration structure built (call optix_build_bvh first)");
+    const mcs_tensor *all[] = {mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms};
+    for (const mcs_tensor *t : all) MCS_REQUIRE(view_ok(t), "env_shade: null / empty tensor argument");
+    MCS_REQUIRE(bsdf <= 2u, "env_shade: BSDF must be 0 ('pbr'), 1 ('diffuse') or 2 ('white')");
+    MCS_REQUIRE(n_samples_x >= 1u && n_samples_x <= 64u, "env_shade: n_samples_x must be in [1, 64]");
+    p.B = ro->sizes[0]; p.H = ro->sizes[1]; p.W = ro->sizes[2];
+    MCS_REQUIRE(ro->sizes[3] == 3, "env_shade: ro must be [B,H,W,3]");
+    MCS_REQUIRE((int64_t)p.B * p.H * p.W < (1ll << 31) / 3, "env_shade: launch too large for 32-bit indexing");
+    const mcs_tensor *gb[] = {mask, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks};
+    const char *gbn[] = {"mask", "gb_pos", "gb_normal", "gb_view_pos", "gb_kd", "gb_ks"};
+    for (int i = 0; i < 6; ++i) {
+        for (int d = 0; d < 3; ++d)
+            MCS_REQUIRE(gb[i]->sizes[d] == ro->sizes[d] || gb[i]->sizes[d] == 1, "env_shade: %s dim %d = %d is not broadcastable to %d", gbn[i], d,
+                        gb[i]->sizes[d], ro->sizes[d]);
+        MCS_REQUIRE(gb[i]->sizes[3] == (i == 0 ? 1 : 3) || gb[i]->sizes[3] == 1, "env_shade: %s has a bad channel count %d", gbn[i], gb[i]->sizes[3]);
+    }
+    p.mask = make_view(mask); p.ro = make_view(ro); p.pos = make_view(gb_pos); p.nrm = make_view(gb_normal);
+    p.view = make_view(gb_view_pos); p.kd = make_view(gb_kd); p.ks = make_view(gb_ks);
+    p.Hl = light->sizes[1]; p.Wl = light->sizes[2];
+    MCS_REQUIRE(light->sizes[3] == 3 && p.Hl >= 2 && p.Wl >= 2, "env_shade: light must be [Hl>=2, Wl>=2, 3]");
+    MCS_REQUIRE(p.Hl < 32768 && p.Wl < 65536, "env_shade: light probe too large");
+    MCS_REQUIRE(pdf->sizes[1] == p.Hl && pdf->sizes[2] == p.Wl && cols->sizes[1] == p.Hl && cols->sizes[2] == p.Wl && rows->sizes[1] == p.Hl,
+                "env_shade: pdf / rows / cols do not match the light probe resolution");
+    p.light = (const float *)light->ptr; p.l_s1 = light->strides[1]; p.l_s2 = light->strides[2]; p.l_s3 = light->strides[3];
+    p.pdf = (const float *)pdf->ptr; p.p_s1 = pdf->strides[1]; p.p_s2 = pdf->strides[2];
+    p.rows = (const float *)rows->ptr; p.r_s = rows->strides[1];
+    p.cols = (const float *)cols->ptr; p.c_s1 = cols->strides[1]; p.c_s2 = cols->strides[2];
+    p.N = (int)n_samples_x; p.S = p.N * p.N;
+    MCS_REQUIRE(perms->sizes[3] == p.S && perms->sizes[1] >= 1, "env_shade: perms must be [P, n_samples_x^2]");
+    p.perms = (const int32_t *)perms->ptr; p.pm_s1 = perms->strides[1]; p.pm_s3 = perms->strides[3]; p.n_perms = (uint32_t)perms->sizes[1];
+    p.m_rows = cdf_iters(p.Hl); p.m_cols = cdf_iters(p.Wl);
+    p.bsdf = bsdf; p.seed = rnd_seed; p.batch_offset = batch_offset; p.shadow_scale = shadow_scale;
+    p.bvh = BvhView{(const float4 *)ctx->nodes.p, (const float4 *)ctx->tris.p};
+    if (int e = ensure_skip_table(ctx, p.N, s)) return e;
+    p.skip = (const uint2 *)((const char *)ctx->lcg_skip.p);
+    if (int e = mcs_buf_reserve(ctx->light_grad4, 256, s)) return e;
+    p.chunk_counter = (unsigned int *)ctx->light_grad4.p;
+    MCS_CUDA(cudaMemsetAsync(p.chunk_counter, 0, sizeof(unsigned int), s));
+    return 0;
+}
+
+template <int MODE>
+static int launch_env(const EnvParams &p, cudaStream_t s)
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    MCS_CUDA(cudaGetDevice(&dev));
+    MCS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, env_shade_kernel<MODE>, WARPS_PER_CTA * 32, 0));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t npix = (int64_t)p.B * p.H * p.W;
+    int64_t want = (npix + 32 * WARPS_PER_CTA - 1) / (32 * WARPS_PER_CTA);
+    int grid = (int)(want < (int64_t)sms * per_sm ? want : (int64_t)sms * per_sm);
+    if (grid < 1) grid = 1;
+    env_shade_kernel<MODE><<<grid, WARPS_PER_CTA * 32, 0, s>>>(p);
+    MCS_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mcs_env_shade_fwd(mcs_ctx *ctx,
+                      const mcs_tensor *mask, const mcs_tensor *ro, const mcs_tensor *gb_pos, const mcs_tensor *gb_normal,
+                      const mcs_tensor *gb_view_pos, const mcs_tensor *gb_kd, const mcs_tensor *gb_ks,
+                      const mcs_tensor *light, const mcs_tensor *pdf, const mcs_tensor *rows, const mcs_tensor *cols,
+                      const mcs_tensor *perms,
+                      uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
+                      float *diff, float *spec, mcs_stream stream)
+{
+    EnvParams p{};
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int e = fill_params(ctx, p, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms, bsdf, n_samples_x, rnd_seed,
+                            shadow_scale, batch_offset, s)) return e;
+    MCS_REQUIRE(diff && spec, "env_shade_fwd: null output pointer");
+    p.diff = diff; p.spec = spec;
+    return launch_env<0>(p, s);
+}
+
+int mcs_env_shade_records(mcs_ctx *ctx,
+                          const mcs_tensor *mask, const mcs_tensor *ro, const mcs_tensor *gb_pos, const mcs_tensor *gb_normal,
+                          const mcs_tensor *gb_view_pos, const mcs_tensor *gb_kd, const mcs_tensor *gb_ks,
+                          const mcs_tensor *light, const mcs_tensor *pdf, const mcs_tensor *rows, const mcs_tensor *cols,
+                          const mcs_tensor *perms,
+                          uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
+                          float *diff, float *spec, int32_t *rec_texel, uint8_t *rec_vis, mcs_stream stream)
+{
+    EnvParams p{};
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int e = fill_params(ctx, p, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms, bsdf, n_samples_x, rnd_seed,
+                            shadow_scale, batch_offset, s)) return e;
+    MCS_REQUIRE(diff && spec && rec_texel && rec_vis, "env_shade_records: null output pointer");
+    p.diff = diff; p.spec = spec; p.rec_texel = rec_texel; p.rec_vis = rec_vis;
+    return launch_env<2>(p, s);
+}
+
+int mcs_env_shade_bwd(mcs_ctx *ctx,
+                      const mcs_tensor *mask, const mcs_tensor *ro, const mcs_tensor *gb_pos, const mcs_tensor *gb_normal,
+                      const mcs_tensor *gb_view_pos, const mcs_tensor *gb_kd, const mcs_tensor *gb_ks,
+                      const mcs_tensor *light, const mcs_tensor *pdf, const mcs_tensor *rows, const mcs_tensor *cols,
+                      const mcs_tensor *perms,
+                      uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
+                      const mcs_tensor *diff_grad, const mcs_tensor *spec_grad,
+                      float *gb_pos_grad, float *gb_normal_grad, float *gb_kd_grad, float *gb_ks_grad, float *light_grad,
+                      mcs_stream stream)
+{
+    EnvParams p{};
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int e = fill_params(ctx, p, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms, bsdf, n_samples_x, rnd_seed,
+                            shadow_scale, batch_offset, s)) return e;
+    MCS_REQUIRE(view_ok(diff_grad) && view_ok(spec_grad), "env_shade_bwd: null / empty upstream gradient");
+    MCS_REQUIRE(gb_pos_grad && gb_normal_grad && gb_kd_grad && gb_ks_grad && light_grad, "env_shade_bwd: null output pointer");
+    for (int d = 0; d < 3; ++d)
+        MCS_REQUIRE(diff_grad->sizes[d] == ro->sizes[d] && spec_grad->sizes[d] == ro->sizes[d], "env_shade_bwd: upstream gradient shape mismatch");
+    p.diff_grad = make_view(diff_grad); p.spec_grad = make_view(spec_grad);
+    p.pos_grad = gb_pos_grad; p.nrm_grad = gb_normal_grad; p.kd_grad = gb_kd_grad; p.ks_grad = gb_ks_grad; p.light_grad = light_grad;
+    MCS_CUDA(cudaMemsetAsync(light_grad, 0, sizeof(float) * 3 * (size_t)p.Hl * p.Wl, s));
+    return launch_env<1>(p, s);
+}
+
+}  // extern "C"

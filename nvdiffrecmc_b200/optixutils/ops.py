@@ -1,0 +1,251 @@
+"""Drop-in replacement for render/optixutils/ops.py (reference lines cited per function).
+
+Same names, argument order and meaning; differences are deliberate fixes listed in SURVEY.md
+appendix A: nothing is JIT-compiled at import, CUDA errors raise RuntimeError, no host
+synchronisation, the BVH build runs on the current stream, no OptiX / NVRTC / RT cores.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+
+_BSDF_MODES = ['pbr', 'diffuse', 'white']      # ops.py:136 -- order matters, it is the kernel's enum
+
+
+def _f32(t, name):
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32 (got %s)" % (name, t.dtype))
+    return t
+
+
+# ----------------------------------------------------------------------------------------------
+# Context: replaces OptiXContext / OptiXStateWrapper (ops.py:125-128)
+# ----------------------------------------------------------------------------------------------
+class OptiXContext:
+    """Opaque per-scene state owning the acceleration structure.  `cpp_wrapper` is kept as the
+    attribute name the reference's callers see (ops.py:128); here it is the C-ABI context handle."""
+
+    def __init__(self):
+        h = C.c_void_p()
+        L.check(L.lib().mcs_ctx_create(C.byref(h)), "mcs_ctx_create")
+        self.cpp_wrapper = h
+        self._geom = None        # keeps verts/tris alive: the build is asynchronous
+
+    def __del__(self):
+        try:
+            if getattr(self, "cpp_wrapper", None) is not None and self.cpp_wrapper.value:
+                torch.cuda.synchronize()
+                L.lib().mcs_ctx_destroy(self.cpp_wrapper)
+                self.cpp_wrapper = None
+        except Exception:
+            pass
+
+
+def optix_build_bvh(optix_ctx, verts, tris, rebuild):
+    """ops.py:130-133.  verts fp32 [V,3], tris int32 [T,3] (CUDA).  rebuild=0 refits boxes only."""
+    assert tris.shape[0] > 0, "Got empty training triangle mesh (unrecoverable discontinuity)"
+    assert verts.shape[0] > 0, "Got empty training triangle mesh (unrecoverable discontinuity)"
+    L.require_cuda(verts, tris)
+    v = _f32(verts, "verts").reshape(-1, 3).contiguous()
+    if tris.dtype != torch.int32:
+        raise RuntimeError("tris must be int32 (the reference's callers do .int(), geometry/dlmesh.py:50)")
+    t = tris.reshape(-1, 3).contiguous()
+    optix_ctx._geom = (v, t)
+    L.check(L.lib().mcs_bvh_build(optix_ctx.cpp_wrapper, v.data_ptr(), v.shape[0], t.data_ptr(), t.shape[0], int(rebuild), L.stream_ptr()),
+            "optix_build_bvh")
+
+
+def _env_descs(mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms):
+    L.require_cuda(mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms)
+    for n, t in (("mask", mask), ("ro", ro), ("gb_pos", gb_pos), ("gb_normal", gb_normal), ("gb_view_pos", gb_view_pos), ("gb_kd", gb_kd),
+                 ("gb_ks", gb_ks), ("light", light), ("pdf", pdf), ("rows", rows), ("cols", cols)):
+        _f32(t, n)
+    if perms.dtype != torch.int32:
+        raise RuntimeError("perms must be int32")
+    d = [L.nhw1(mask), L.nhwc(ro), L.nhwc(gb_pos), L.nhwc(gb_normal), L.nhwc(gb_view_pos), L.nhwc(gb_kd), L.nhwc(gb_ks),
+         L.view_hwc(light), L.view_hw(pdf), L.view_h(rows), L.view_hw(cols), L.view_perms(perms)]
+    return d
+
+
+class _optix_env_shade_func(torch.autograd.Function):
+    """ops.py:78-105"""
+    _random_perm = {}
+
+    @staticmethod
+    def get_perms(n_samples_x, device):
+        key = (n_samples_x, str(device))
+        if key not in _optix_env_shade_func._random_perm:
+            # (32k) tables with random permutations to decorrelate BSDF and light strata (ops.py:84-86)
+            _optix_env_shade_func._random_perm[key] = torch.argsort(
+                torch.rand(32768, n_samples_x * n_samples_x, device=device), dim=-1).int()
+        return _optix_env_shade_func._random_perm[key]
+
+    @staticmethod
+    def forward(ctx, optix_ctx, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, BSDF, n_samples_x, rnd_seed,
+                shadow_scale, perms, batch_offset):
+        _rnd_seed = np.random.randint(2**31) if rnd_seed is None else rnd_seed
+        if perms is None:
+            perms = _optix_env_shade_func.get_perms(n_samples_x, ro.device)
+        d = _env_descs(mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms)
+        B, H, W = ro.shape[0], ro.shape[1], ro.shape[2]
+        diff = torch.empty(B, H, W, 3, dtype=torch.float32, device=ro.device)
+        spec = torch.empty(B, H, W, 3, dtype=torch.float32, device=ro.device)
+        L.check(L.lib().mcs_env_shade_fwd(optix_ctx.cpp_wrapper, *[C.byref(x) for x in d], int(BSDF), int(n_samples_x),
+                                          int(_rnd_seed) & 0xFFFFFFFF, float(shadow_scale), int(batch_offset),
+                                          diff.data_ptr(), spec.data_ptr(), L.stream_ptr()), "optix_env_shade (forward)")
+        ctx.save_for_backward(mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms)
+        ctx.optix_ctx = optix_ctx
+        ctx.BSDF = BSDF
+        ctx.n_samples_x = n_samples_x
+        ctx.rnd_seed = rnd_seed
+        ctx.shadow_scale = shadow_scale
+        ctx.batch_offset = batch_offset
+        return diff, spec
+
+    @staticmethod
+    def backward(ctx, diff_grad, spec_grad):
+        optix_ctx = ctx.optix_ctx
+        # decorrelated mode draws an independent seed for the backward pass (ops.py:100)
+        _rnd_seed = np.random.randint(2**31) if ctx.rnd_seed is None else ctx.rnd_seed
+        mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms = ctx.saved_tensors
+        d = _env_descs(mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms)
+        B, H, W = ro.shape[0], ro.shape[1], ro.shape[2]
+        dev = ro.device
+        g = [torch.empty(B, H, W, 3, dtype=torch.float32, device=dev) for _ in range(4)]
+        light_grad = torch.empty(light.shape[0], light.shape[1], 3, dtype=torch.float32, device=dev)
+        dg, sg = L.nhwc(diff_grad.float()), L.nhwc(spec_grad.float())
+        L.check(L.lib().mcs_env_shade_bwd(optix_ctx.cpp_wrapper, *[C.byref(x) for x in d], int(ctx.BSDF), int(ctx.n_samples_x),
+                                          int(_rnd_seed) & 0xFFFFFFFF, float(ctx.shadow_scale), int(ctx.batch_offset),
+                                          C.byref(dg), C.byref(sg), g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), g[3].data_ptr(),
+                                          light_grad.data_ptr(), L.stream_ptr()), "optix_env_shade (backward)")
+        # same gradient slots as ops.py:105 (no gradient for ro / view_pos / pdf / rows / cols)
+        return (None, None, None, g[0], g[1], None, g[2], g[3], light_grad, None, None, None, None, None, None, None, None, None)
+
+
+def optix_env_shade(optix_ctx, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, BSDF='pbr', n_samples_x=8,
+                    rnd_seed=None, shadow_scale=1.0, perms=None, batch_offset=0):
+    """ops.py:135-137.  Extra keyword-only-in-spirit arguments (defaults reproduce the reference):
+    perms        -- inject the [P, n^2] int32 permutation table (the reference draws it once from the unseeded CUDA RNG)
+    batch_offset -- index of this rank's first view in the global batch (data-parallel RNG parity, kernel.cu:504)"""
+    iBSDF = _BSDF_MODES.index(BSDF)
+    return _optix_env_shade_func.apply(optix_ctx, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, iBSDF,
+                                       n_samples_x, rnd_seed, shadow_scale, perms, batch_offset)
+
+
+def env_shade_records(optix_ctx, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms, BSDF='pbr',
+                      n_samples_x=8, rnd_seed=0, shadow_scale=1.0, batch_offset=0):
+    """Parity hook: forward pass + per-ray records (env texel, visibility).  See mcs_env_shade_records."""
+    d = _env_descs(mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms)
+    B, H, W = ro.shape[0], ro.shape[1], ro.shape[2]
+    S2 = 2 * n_samples_x * n_samples_x
+    diff = torch.empty(B, H, W, 3, dtype=torch.float32, device=ro.device)
+    spec = torch.empty(B, H, W, 3, dtype=torch.float32, device=ro.device)
+    rec_t = torch.full((B, H, W, S2), -1, dtype=torch.int32, device=ro.device)
+    rec_v = torch.full((B, H, W, S2), 255, dtype=torch.uint8, device=ro.device)
+    L.check(L.lib().mcs_env_shade_records(optix_ctx.cpp_wrapper, *[C.byref(x) for x in d], _BSDF_MODES.index(BSDF), int(n_samples_x),
+                                          int(rnd_seed) & 0xFFFFFFFF, float(shadow_scale), int(batch_offset), diff.data_ptr(), spec.data_ptr(),
+                                          rec_t.data_ptr(), rec_v.data_ptr(), L.stream_ptr()), "env_shade_records")
+    return diff, spec, rec_t, rec_v
+
+
+# ----------------------------------------------------------------------------------------------
+# Ray queries outside the fused kernel (parity tests, synthetic G-buffer producer)
+# ----------------------------------------------------------------------------------------------
+def trace_visibility(optix_ctx, ro, rd):
+    """uint8 [n]: 1 if the ray (origin ro[n,3], direction rd[n,3], t in (0,1e16)) hits nothing."""
+    L.require_cuda(ro, rd)
+    ro = _f32(ro, "ro").reshape(-1, 3).contiguous(); rd = _f32(rd, "rd").reshape(-1, 3).contiguous()
+    vis = torch.empty(ro.shape[0], dtype=torch.uint8, device=ro.device)
+    L.check(L.lib().mcs_trace_visibility(optix_ctx.cpp_wrapper, ro.data_ptr(), rd.data_ptr(), ro.shape[0], vis.data_ptr(), L.stream_ptr()),
+            "trace_visibility")
+    return vis
+
+
+def trace_closest(optix_ctx, ro, rd):
+    """(tri_id int32 [n] (-1 = miss), tuv fp32 [n,3] = (t, u, v))"""
+    L.require_cuda(ro, rd)
+    ro = _f32(ro, "ro").reshape(-1, 3).contiguous(); rd = _f32(rd, "rd").reshape(-1, 3).contiguous()
+    tid = torch.empty(ro.shape[0], dtype=torch.int32, device=ro.device)
+    tuv = torch.empty(ro.shape[0], 3, dtype=torch.float32, device=ro.device)
+    L.check(L.lib().mcs_trace_closest(optix_ctx.cpp_wrapper, ro.data_ptr(), rd.data_ptr(), ro.shape[0], tid.data_ptr(), tuv.data_ptr(),
+                                      L.stream_ptr()), "trace_closest")
+    return tid, tuv
+
+
+def bvh_export(optix_ctx):
+    """Binary LBVH arrays (sorted Morton keys, prim ids, children, padded boxes) for structural parity tests."""
+    T = optix_ctx._geom[1].shape[0]
+    dev = optix_ctx._geom[0].device
+    morton = torch.empty(T, dtype=torch.int32, device=dev); prim = torch.empty(T, dtype=torch.int32, device=dev)
+    left = torch.empty(max(T - 1, 1), dtype=torch.int32, device=dev); right = torch.empty(max(T - 1, 1), dtype=torch.int32, device=dev)
+    lo = torch.empty(2 * T - 1, 3, dtype=torch.float32, device=dev); hi = torch.empty(2 * T - 1, 3, dtype=torch.float32, device=dev)
+    L.check(L.lib().mcs_bvh_export(optix_ctx.cpp_wrapper, morton.data_ptr(), prim.data_ptr(), left.data_ptr(), right.data_ptr(), lo.data_ptr(),
+                                   hi.data_ptr(), L.stream_ptr()), "bvh_export")
+    return dict(morton=morton, prim=prim, left=left[:T - 1], right=right[:T - 1], lo=lo, hi=hi)
+
+
+# ----------------------------------------------------------------------------------------------
+# Bilateral denoiser (ops.py:107-119, 139-141)
+# ----------------------------------------------------------------------------------------------
+class _bilateral_denoiser_func(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, col, nrm, zdz, sigma):
+        L.require_cuda(col, nrm, zdz)
+        ctx.save_for_backward(nrm, zdz)
+        ctx.sigma = sigma
+        B, H, W = col.shape[0], col.shape[1], col.shape[2]
+        out = torch.empty(B, H, W, 4, dtype=torch.float32, device=col.device)
+        c, n, z = L.nhwc(_f32(col, "col")), L.nhwc(_f32(nrm, "nrm")), L.nhwc(_f32(zdz, "zdz"))
+        L.check(L.lib().mcs_bilateral_fwd(C.byref(c), C.byref(n), C.byref(z), float(sigma), out.data_ptr(), L.stream_ptr()), "bilateral_denoiser (forward)")
+        return out
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        nrm, zdz = ctx.saved_tensors
+        B, H, W = nrm.shape[0], nrm.shape[1], nrm.shape[2]
+        col_grad = torch.empty(B, H, W, 3, dtype=torch.float32, device=nrm.device)
+        n, z, g = L.nhwc(nrm), L.nhwc(zdz), L.nhwc(out_grad.float())
+        L.check(L.lib().mcs_bilateral_bwd(C.byref(n), C.byref(z), float(ctx.sigma), C.byref(g), col_grad.data_ptr(), L.stream_ptr()),
+                "bilateral_denoiser (backward)")
+        return col_grad, None, None, None      # no gradient for nrm / zdz (ops.py:119)
+
+
+def bilateral_denoiser(col, nrm, zdz, sigma):
+    """ops.py:139-141"""
+    col_w = _bilateral_denoiser_func.apply(col, nrm, zdz, sigma)
+    return col_w[..., 0:3] / col_w[..., 3:4]
+
+
+class _bilateral_denoiser2_func(torch.autograd.Function):
+    """Two signals, one set of guides (render.py:120-121 filters diffuse and specular identically)."""
+    @staticmethod
+    def forward(ctx, colA, colB, nrm, zdz, sigma):
+        L.require_cuda(colA, colB, nrm, zdz)
+        ctx.save_for_backward(nrm, zdz)
+        ctx.sigma = sigma
+        B, H, W = colA.shape[0], colA.shape[1], colA.shape[2]
+        outA = torch.empty(B, H, W, 4, dtype=torch.float32, device=colA.device)
+        outB = torch.empty(B, H, W, 4, dtype=torch.float32, device=colA.device)
+        a, b, n, z = L.nhwc(_f32(colA, "colA")), L.nhwc(_f32(colB, "colB")), L.nhwc(_f32(nrm, "nrm")), L.nhwc(_f32(zdz, "zdz"))
+        L.check(L.lib().mcs_bilateral_fwd2(C.byref(a), C.byref(b), C.byref(n), C.byref(z), float(sigma), outA.data_ptr(), outB.data_ptr(),
+                                           L.stream_ptr()), "bilateral_denoiser2 (forward)")
+        return outA, outB
+
+    @staticmethod
+    def backward(ctx, gA, gB):
+        nrm, zdz = ctx.saved_tensors
+        B, H, W = nrm.shape[0], nrm.shape[1], nrm.shape[2]
+        cA = torch.empty(B, H, W, 3, dtype=torch.float32, device=nrm.device)
+        cB = torch.empty(B, H, W, 3, dtype=torch.float32, device=nrm.device)
+        n, z, a, b = L.nhwc(nrm), L.nhwc(zdz), L.nhwc(gA.float()), L.nhwc(gB.float())
+        L.check(L.lib().mcs_bilateral_bwd2(C.byref(n), C.byref(z), float(ctx.sigma), C.byref(a), C.byref(b), cA.data_ptr(), cB.data_ptr(),
+                                           L.stream_ptr()), "bilateral_denoiser2 (backward)")
+        return cA, cB, None, None, None
+
+
+def bilateral_denoiser2(colA, colB, nrm, zdz, sigma):
+    """Fused equivalent of (bilateral_denoiser(colA, ...), bilateral_denoiser(colB, ...))."""
+    a, b = _bilateral_denoiser2_func.apply(colA, colB, nrm, zdz, sigma)
+    return a[..., 0:3] / a[..., 3:4], b[..., 0:3] / b[..., 3:4]

@@ -1,0 +1,235 @@
+"""Drop-in replacement for the BSDF / shading-normal part of render/renderutils/ops.py.
+
+Every op keeps the reference signature including the `use_python=` validation switch
+(renderutils/ops.py:101,124,146,168,194,244,278,315,355); the CUDA path calls libmcshade through the
+C ABI.  Gradients of broadcast inputs come back full-size from the kernel and are reduced by
+`_reduce_like` (the reference leaves that to autograd's sum_to_size, tensor.h:61,75).
+"""
+import ctypes as C
+
+import torch
+
+from .. import _lib as L
+from . import bsdf as _tb
+
+
+def _prep(*ts):
+    L.require_cuda(*ts)
+    out = []
+    for t in ts:
+        if t.dim() != 4:
+            raise RuntimeError("expected [minibatch, height, width, channels] tensors, got shape %s" % (tuple(t.shape),))
+        out.append(t if t.dtype == torch.float32 else t.float())
+    return out
+
+
+def _grid(*ts):
+    return tuple(max(t.shape[d] for t in ts) for d in range(3))
+
+
+def _reduce_like(g, ref):
+    """Sum a full-grid gradient down to the (broadcast) shape of its input."""
+    if tuple(g.shape) == tuple(ref.shape):
+        return g
+    return g.sum_to_size(ref.shape)
+
+
+def _call(name, ins, extra, n_out_ch, dout=None):
+    """Run mcs_<name>: ins (+ dout) as mcs_tensor views, outputs freshly allocated contiguous fp32."""
+    ins = _prep(*ins)
+    allt = ins + (_prep(dout) if dout is not None else [])
+    N, H, W = _grid(*allt)
+    outs = [torch.empty(N, H, W, c, dtype=torch.float32, device=ins[0].device) for c in n_out_ch]
+    descs = [L.nhwc(t) for t in ins]
+    args = [C.byref(d) for d in descs] + list(extra)
+    if dout is not None:
+        dd = L.nhwc(allt[-1])
+        args.append(C.byref(dd))
+    args += [o.data_ptr() for o in outs] + [L.stream_ptr()]
+    L.check(getattr(L.lib(), "mcs_" + name)(*args), name)
+    return outs
+
+
+def _finite(out, name):
+    if torch.is_anomaly_enabled():
+        assert torch.all(torch.isfinite(out)), "Output of %s contains inf or NaN" % name
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+class _fresnel_shlick_func(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f0, f90, cosTheta):
+        ctx.save_for_backward(f0, f90, cosTheta)
+        return _call("fresnel_shlick_fwd", [f0, f90, cosTheta], [], [3])[0]
+
+    @staticmethod
+    def backward(ctx, dout):
+        ins = ctx.saved_tensors
+        g = _call("fresnel_shlick_bwd", ins, [], [3, 3, 1], dout=dout)
+        return tuple(_reduce_like(a, b) for a, b in zip(g, ins))
+
+
+def _fresnel_shlick(f0, f90, cosTheta, use_python=False):
+    """renderutils/ops.py:89-109"""
+    out = _tb.fresnel_schlick(f0, f90, cosTheta) if use_python else _fresnel_shlick_func.apply(f0, f90, cosTheta)
+    return _finite(out, "_fresnel_shlick")
+
+
+class _ggx2_func(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, which, alphaSqr, cosTheta):
+        ctx.which = which
+        ctx.save_for_backward(alphaSqr, cosTheta)
+        return _call(which + "_fwd", [alphaSqr, cosTheta], [], [1])[0]
+
+    @staticmethod
+    def backward(ctx, dout):
+        ins = ctx.saved_tensors
+        g = _call(ctx.which + "_bwd", ins, [], [1, 1], dout=dout)
+        return (None,) + tuple(_reduce_like(a, b) for a, b in zip(g, ins))
+
+
+def _ndf_ggx(alphaSqr, cosTheta, use_python=False):
+    """renderutils/ops.py:112-132"""
+    out = _tb.ndf_ggx(alphaSqr, cosTheta) if use_python else _ggx2_func.apply("ndf_ggx", alphaSqr, cosTheta)
+    return _finite(out, "_ndf_ggx")
+
+
+def _lambda_ggx(alphaSqr, cosTheta, use_python=False):
+    """renderutils/ops.py:134-154"""
+    out = _tb.lambda_ggx(alphaSqr, cosTheta) if use_python else _ggx2_func.apply("lambda_ggx", alphaSqr, cosTheta)
+    return _finite(out, "_lambda_ggx")
+
+
+class _masking_smith_func(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, alphaSqr, cosThetaI, cosThetaO):
+        ctx.save_for_backward(alphaSqr, cosThetaI, cosThetaO)
+        return _call("masking_smith_fwd", [alphaSqr, cosThetaI, cosThetaO], [], [1])[0]
+
+    @staticmethod
+    def backward(ctx, dout):
+        ins = ctx.saved_tensors
+        g = _call("masking_smith_bwd", ins, [], [1, 1, 1], dout=dout)
+        return tuple(_reduce_like(a, b) for a, b in zip(g, ins))
+
+
+def _masking_smith(alphaSqr, cosThetaI, cosThetaO, use_python=False):
+    """renderutils/ops.py:156-176"""
+    out = _tb.masking_smith(alphaSqr, cosThetaI, cosThetaO) if use_python else _masking_smith_func.apply(alphaSqr, cosThetaI, cosThetaO)
+    return _finite(out, "_masking_smith")
+
+
+# ---------------------------------------------------------------------------------------------
+class _prepare_shading_normal_func(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, view_pos, perturbed_nrm, smooth_nrm, smooth_tng, geom_nrm, two_sided_shading, opengl):
+        ctx.two_sided_shading, ctx.opengl = two_sided_shading, opengl
+        ctx.save_for_backward(pos, view_pos, perturbed_nrm, smooth_nrm, smooth_tng, geom_nrm)
+        return _call("prepare_shading_normal_fwd", [pos, view_pos, perturbed_nrm, smooth_nrm, smooth_tng, geom_nrm],
+                     [C.c_int32(int(two_sided_shading)), C.c_int32(int(opengl))], [3])[0]
+
+    @staticmethod
+    def backward(ctx, dout):
+        ins = ctx.saved_tensors
+        g = _call("prepare_shading_normal_bwd", ins, [C.c_int32(int(ctx.two_sided_shading)), C.c_int32(int(ctx.opengl))], [3] * 6, dout=dout)
+        return tuple(_reduce_like(a, b) for a, b in zip(g, ins)) + (None, None)
+
+
+def prepare_shading_normal(pos, view_pos, perturbed_nrm, smooth_nrm, smooth_tng, geom_nrm, two_sided_shading=True, opengl=True, use_python=False):
+    """renderutils/ops.py:181-227.  Builds the tangent frame, perturbs by the normal map, flips for
+    two-sided shading and bends back-facing normals towards the camera.  All tensors are
+    [minibatch, height, width, 3] or broadcastable."""
+    if perturbed_nrm is None:
+        perturbed_nrm = torch.tensor([0, 0, 1], dtype=torch.float32, device=pos.device, requires_grad=False)[None, None, None, ...]
+    if use_python:
+        out = _tb.prepare_shading_normal(pos, view_pos, perturbed_nrm, smooth_nrm, smooth_tng, geom_nrm, two_sided_shading, opengl)
+    else:
+        out = _prepare_shading_normal_func.apply(pos, view_pos, perturbed_nrm, smooth_nrm, smooth_tng, geom_nrm, two_sided_shading, opengl)
+    return _finite(out, "prepare_shading_normal")
+
+
+# ---------------------------------------------------------------------------------------------
+class _lambert_func(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, nrm, wi):
+        ctx.save_for_backward(nrm, wi)
+        return _call("lambert_fwd", [nrm, wi], [], [1])[0]
+
+    @staticmethod
+    def backward(ctx, dout):
+        ins = ctx.saved_tensors
+        g = _call("lambert_bwd", ins, [], [3, 3], dout=dout)
+        return tuple(_reduce_like(a, b) for a, b in zip(g, ins))
+
+
+def lambert(nrm, wi, use_python=False):
+    """renderutils/ops.py:244-264 -> [minibatch, height, width, 1]"""
+    out = _tb.lambert(nrm, wi) if use_python else _lambert_func.apply(nrm, wi)
+    return _finite(out, "lambert")
+
+
+class _frostbite_diffuse_func(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, nrm, wi, wo, linearRoughness):
+        ctx.save_for_backward(nrm, wi, wo, linearRoughness)
+        return _call("frostbite_fwd", [nrm, wi, wo, linearRoughness], [], [1])[0]
+
+    @staticmethod
+    def backward(ctx, dout):
+        ins = ctx.saved_tensors
+        g = _call("frostbite_bwd", ins, [], [3, 3, 3, 1], dout=dout)
+        return tuple(_reduce_like(a, b) for a, b in zip(g, ins))
+
+
+def frostbite_diffuse(nrm, wi, wo, linearRoughness, use_python=False):
+    """renderutils/ops.py:278-300"""
+    out = _tb.frostbite_diffuse(nrm, wi, wo, linearRoughness) if use_python else _frostbite_diffuse_func.apply(nrm, wi, wo, linearRoughness)
+    return _finite(out, "frostbite_diffuse")
+
+
+class _pbr_specular_func(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, col, nrm, wo, wi, alpha, min_roughness):
+        ctx.save_for_backward(col, nrm, wo, wi, alpha)
+        ctx.min_roughness = min_roughness
+        return _call("pbr_specular_fwd", [col, nrm, wo, wi, alpha], [C.c_float(min_roughness)], [3])[0]
+
+    @staticmethod
+    def backward(ctx, dout):
+        ins = ctx.saved_tensors
+        g = _call("pbr_specular_bwd", ins, [C.c_float(ctx.min_roughness)], [3, 3, 3, 3, 1], dout=dout)
+        return tuple(_reduce_like(a, b) for a, b in zip(g, ins)) + (None,)
+
+
+def pbr_specular(col, nrm, wo, wi, alpha, min_roughness=0.08, use_python=False):
+    """renderutils/ops.py:315-339; alpha is [minibatch, height, width, 1]"""
+    out = _tb.pbr_specular(col, nrm, wo, wi, alpha, min_roughness) if use_python else _pbr_specular_func.apply(col, nrm, wo, wi, alpha, min_roughness)
+    return _finite(out, "pbr_specular")
+
+
+class _pbr_bsdf_func(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kd, arm, pos, nrm, view_pos, light_pos, min_roughness, BSDF):
+        ctx.save_for_backward(kd, arm, pos, nrm, view_pos, light_pos)
+        ctx.min_roughness = min_roughness
+        ctx.BSDF = BSDF
+        return _call("pbr_bsdf_fwd", [kd, arm, pos, nrm, view_pos, light_pos], [C.c_float(min_roughness), C.c_int32(BSDF)], [3])[0]
+
+    @staticmethod
+    def backward(ctx, dout):
+        ins = ctx.saved_tensors
+        g = _call("pbr_bsdf_bwd", ins, [C.c_float(ctx.min_roughness), C.c_int32(ctx.BSDF)], [3] * 6, dout=dout)
+        return tuple(_reduce_like(a, b) for a, b in zip(g, ins)) + (None, None)
+
+
+def pbr_bsdf(kd, arm, pos, nrm, view_pos, light_pos, min_roughness=0.08, bsdf="lambert", use_python=False):
+    """renderutils/ops.py:355-386.  Diffuse (Lambert or Frostbite) + GGX specular for a point light.
+    kd: albedo, arm: (occlusion/spec attenuation, linear roughness, metalness)."""
+    BSDF = 1 if bsdf == 'frostbite' else 0
+    if use_python:
+        out = _tb.pbr_bsdf(kd, arm, pos, nrm, view_pos, light_pos, min_roughness, BSDF)
+    else:
+        out = _pbr_bsdf_func.apply(kd, arm, pos, nrm, view_pos, light_pos, min_roughness, BSDF)
+    return _finite(out, "pbr_bsdf")
