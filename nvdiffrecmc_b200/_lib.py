@@ -3,6 +3,7 @@
 The product path has NO fallback: if the shared library is missing or a call fails, a RuntimeError
 is raised (the reference silently drops CUDA/OptiX errors, optixutils/c_src/common.h:37-61).
 """
+import collections
 import ctypes as C
 import os
 import subprocess
@@ -125,7 +126,14 @@ def lib():
     return l
 
 
+# Count of OUR kernels launched through the C ABI (bench.py's gpu_launches claim).  optix_build_bvh launches six hand-written
+# kernels (bounds init, triangle bounds, Morton codes, Karras topology, leaves + refit, node emission) around one CUB radix sort.
+LAUNCHES = collections.Counter()
+_KERNELS_PER_CALL = {"optix_build_bvh": 6}
+
+
 def check(status, what):
+    LAUNCHES[what] += _KERNELS_PER_CALL.get(what, 1)
     if status != 0:
         msg = lib().mcs_last_error()
         raise RuntimeError("%s failed (status %d): %s" % (what, status, msg.decode() if msg else "?"))

@@ -24,6 +24,17 @@ def _lib_path(f64):
     return os.path.join(_BUILD, "libmcoracle_f64.so" if f64 else "libmcoracle_f32.so")
 
 
+def _cpu_has_fma():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return " fma " in (line + " ")
+    except OSError:
+        pass
+    return False
+
+
 def build(force=False):
     """Compile the C restatement with gcc (fp32 + fp64 variants). -ffp-contract=off is mandatory."""
     os.makedirs(_BUILD, exist_ok=True)
@@ -32,13 +43,11 @@ def build(force=False):
         if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in _SRC):
             continue
         cmd = ["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-o", out, _SRC[0], "-lm"]
+        if _cpu_has_fma():
+            cmd.insert(2, "-mfma")       # only the explicit fmaf()/fma() calls of mt_eval use it (contraction stays off)
         if f64:
             cmd.insert(1, "-DORACLE_F64")
         subprocess.run(cmd, check=True)
-
-
-class _EnvShade32(C.Structure):
-    pass
 
 
 def _envshade_struct(real):
@@ -47,7 +56,7 @@ def _envshade_struct(real):
         _fields_ = [
             ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Hl", C.c_int32), ("Wl", C.c_int32),
             ("n_perms", C.c_int32), ("N", C.c_int32), ("bsdf", C.c_int32), ("seed", C.c_uint32),
-            ("batch_offset", C.c_int32), ("backward", C.c_int32), ("vis_mode", C.c_int32), ("shadow_scale", real),
+            ("batch_offset", C.c_int32), ("backward", C.c_int32), ("vis_mode", C.c_int32), ("parallel_bwd", C.c_int32), ("shadow_scale", real),
             ("mask", C.c_void_p), ("ro", C.c_void_p), ("pos", C.c_void_p), ("nrm", C.c_void_p), ("view", C.c_void_p),
             ("kd", C.c_void_p), ("ks", C.c_void_p),
             ("light", C.c_void_p), ("pdf", C.c_void_p), ("rows", C.c_void_p), ("cols", C.c_void_p),
@@ -144,16 +153,6 @@ class Oracle:
         return Scene(self, verts, tris)
 
     # ------------------------------------------------------------------ elementwise ops
-    def _ew(self, name, ins, chans, extra, outs_ch, lead=None):
-        lead, arrs = self._bc(*ins, chans=chans)
-        n = int(np.prod(lead)) if len(lead) else 1
-        outs = [np.zeros(lead + (c,), self.dt) for c in outs_ch]
-        fn = getattr(self.lib, name)
-        args = [C.c_int(n)] + [C.c_void_p(a.ctypes.data) for a in arrs]
-        for e in extra:
-            args.append(self.real(e) if isinstance(e, float) else C.c_int(int(e)))
-        return fn, args, outs
-
     def _run(self, name, ins, chans, extra, outs_ch, extra_after_ins=True, dout=None, dout_ch=None):
         allin = list(ins) + ([dout] if dout is not None else [])
         allch = list(chans) + ([dout_ch] if dout is not None else [])
@@ -243,7 +242,7 @@ class Oracle:
     # ------------------------------------------------------------------ env shade
     def env_shade(self, scene, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms,
                   BSDF="pbr", n_samples_x=8, rnd_seed=0, shadow_scale=1.0, batch_offset=0, vis_mode="brute",
-                  grads=None, records=False, counters=False):
+                  grads=None, records=False, counters=False, parallel_bwd=False):
         """Forward (grads=None) -> (diff, spec[, records][, counters]);
         backward (grads=(diff_grad, spec_grad)) -> (pos_grad, nrm_grad, kd_grad, ks_grad, light_grad).
         Mirrors env_shade_fwd / env_shade_bwd, render/optixutils/c_src/torch_bindings.cpp:123-272."""
@@ -266,6 +265,7 @@ class Oracle:
         p.batch_offset = int(batch_offset)
         p.vis_mode = 2 if scene is None else {"brute": 0, "bvh": 1, "none": 2}[vis_mode]
         p.shadow_scale = float(shadow_scale)
+        p.parallel_bwd = int(parallel_bwd)
         keep = [mask, ro, pos, nrm, view, kd, ks, light, pdf, rows, cols, perms]
         p.mask, p.ro, p.pos, p.nrm, p.view, p.kd, p.ks = [a.ctypes.data for a in (mask, ro, pos, nrm, view, kd, ks)]
         p.light, p.pdf, p.rows, p.cols, p.perms = [a.ctypes.data for a in (light, pdf, rows, cols, perms)]
