@@ -4,19 +4,25 @@
 //   render/renderutils/c_src/bsdf.cu:17-377    (stand-alone ops, kd-modulated, light position)
 // written for sm_100a: everything stays in registers, FMA contraction allowed (this is NOT on the
 // sampling decision path), pow(x,5)/pow(x,3) expanded into multiplies, 1/pi folded into constants.
+//
+// Conditioning note: the GGX NDF denominator d = (c*a2 - c)*c + 1 cancels catastrophically at the
+// specular peak (c -> 1, small roughness): in fp32 its relative rounding noise reaches ~1e-3, and the
+// adjoint (~1/d^3) amplifies it further.  That noise is inherent to the reference's formula; to keep
+// parity testable the half vector, n.h, the gate cosines and every expression containing d are
+// evaluated with exact.cuh arithmetic in the oracle's operation order, so both sides carry the SAME
+// rounding.  Everything else (Fresnel, masking, products, adjoint chains) is well conditioned and
+// uses contracted fast math.
 #pragma once
 #include "common.cuh"
+#include "exact.cuh"
 
 #define MCS_SPEC_EPS 1e-4f
 #define MCS_PI 3.14159265358979323846f
 #define MCS_INV_PI 0.31830988618379067154f
 
-__device__ __forceinline__ f3 safe_normalize(f3 v)
-{
-    float l2 = dot(v, v);
-    float l = sqrtf(l2);
-    return l > 0.0f ? v * (1.0f / l) : F3(0.0f);
-}
+// v / |v| with IEEE sqrt and divisions in the reference's order (math_utils.h:135-139)
+__device__ __forceinline__ f3 safe_normalize(f3 v) { return toF3(xnormalize(X3(v))); }
+__device__ __forceinline__ float dot_exact(f3 a, f3 b) { return xdot(X3(a), X3(b)).v; }
 // adjoint of v / |v|   (math_utils.h:141-152)
 __device__ __forceinline__ void bwd_safe_normalize(f3 v, f3 &d_v, f3 d_out)
 {
@@ -93,19 +99,21 @@ __device__ __forceinline__ void bwd_fresnel3(f3 f0, f3 f90, float cosTheta, f3 &
 // ---- GGX NDF (bsdf.h:76-93) -----------------------------------------------------------------
 __device__ __forceinline__ float fwd_ndf_ggx(float alphaSqr, float cosTheta)
 {
-    float c = clampf(cosTheta, MCS_SPEC_EPS, 1.0f - MCS_SPEC_EPS);
-    float d = (c * alphaSqr - c) * c + 1.0f;
-    return alphaSqr / (d * d * MCS_PI);
+    xf a2 = xf(alphaSqr);
+    xf c = xclamp(xf(cosTheta), xf(MCS_SPEC_EPS), xf(1.0f) - xf(MCS_SPEC_EPS));
+    xf d = (c * a2 - c) * c + xf(1.0f);
+    return (a2 / (d * d * xf(MCS_PI))).v;
 }
 __device__ __forceinline__ void bwd_ndf_ggx(float alphaSqr, float cosTheta, float &d_alphaSqr, float &d_cos, float d_out)
 {
-    float c = clampf(cosTheta, MCS_SPEC_EPS, 1.0f - MCS_SPEC_EPS);
-    float c2 = c * c;
-    float den = (alphaSqr - 1.0f) * c2 + 1.0f;
-    float inv = 1.0f / (MCS_PI * den * den * den);
-    d_alphaSqr += d_out * (1.0f - (alphaSqr + 1.0f) * c2) * inv;
+    xf a2 = xf(alphaSqr);
+    xf c = xclamp(xf(cosTheta), xf(MCS_SPEC_EPS), xf(1.0f) - xf(MCS_SPEC_EPS));
+    xf c2 = c * c;
+    xf den = (a2 - xf(1.0f)) * c2 + xf(1.0f);
+    xf den3 = den * den * den;
+    d_alphaSqr += (xf(d_out) * (xf(1.0f) - (a2 + xf(1.0f)) * c2) / (xf(MCS_PI) * den3)).v;
     if (cosTheta > MCS_SPEC_EPS && cosTheta < 1.0f - MCS_SPEC_EPS)
-        d_cos += d_out * -(4.0f * (alphaSqr - 1.0f) * alphaSqr * cosTheta) * inv;
+        d_cos += (xf(d_out) * -(xf(4.0f) * (a2 - xf(1.0f)) * a2 * xf(cosTheta)) / (xf(MCS_PI) * den3)).v;
 }
 
 // ---- Smith lambda / masking (bsdf.h:98-139) --------------------------------------------------
@@ -140,12 +148,12 @@ __device__ __forceinline__ void bwd_masking_smith(float alphaSqr, float cosI, fl
 // ---- GGX specular lobe (bsdf.h:144-217) ------------------------------------------------------
 __device__ __forceinline__ f3 fwd_pbr_specular(f3 col, f3 nrm, f3 wo, f3 wi, float alpha, float min_roughness)
 {
-    float woDotN = dot(wo, nrm), wiDotN = dot(wi, nrm);
+    float woDotN = dot_exact(wo, nrm), wiDotN = dot_exact(wi, nrm);
     if (!((woDotN > MCS_SPEC_EPS) & (wiDotN > MCS_SPEC_EPS))) return F3(0.0f);
-    float a = clampf(alpha, min_roughness * min_roughness, 1.0f);
-    float alphaSqr = a * a;
-    f3 h = safe_normalize(wo + wi);
-    float woDotH = dot(wo, h), nDotH = dot(nrm, h);
+    float a = clampf(alpha, __fmul_rn(min_roughness, min_roughness), 1.0f);
+    float alphaSqr = __fmul_rn(a, a);
+    f3 h = safe_normalize(F3(__fadd_rn(wo.x, wi.x), __fadd_rn(wo.y, wi.y), __fadd_rn(wo.z, wi.z)));
+    float woDotH = dot_exact(wo, h), nDotH = dot_exact(nrm, h);
     float D = fwd_ndf_ggx(alphaSqr, nDotH);
     float G = fwd_masking_smith(alphaSqr, woDotN, wiDotN);
     f3 F = fwd_fresnel3(col, F3(1.0f), woDotH);
@@ -154,13 +162,13 @@ __device__ __forceinline__ f3 fwd_pbr_specular(f3 col, f3 nrm, f3 wo, f3 wi, flo
 __device__ __forceinline__ void bwd_pbr_specular(f3 col, f3 nrm, f3 wo, f3 wi, float alpha, float min_roughness,
                                                  f3 &d_col, f3 &d_nrm, f3 &d_wo, f3 &d_wi, float &d_alpha, f3 d_out)
 {
-    float woDotN = dot(wo, nrm), wiDotN = dot(wi, nrm);
+    float woDotN = dot_exact(wo, nrm), wiDotN = dot_exact(wi, nrm);
     if (!((woDotN > MCS_SPEC_EPS) & (wiDotN > MCS_SPEC_EPS))) return;
-    float a = clampf(alpha, min_roughness * min_roughness, 1.0f);
-    float alphaSqr = a * a;
-    f3 hsum = wo + wi;
+    float a = clampf(alpha, __fmul_rn(min_roughness, min_roughness), 1.0f);
+    float alphaSqr = __fmul_rn(a, a);
+    f3 hsum = F3(__fadd_rn(wo.x, wi.x), __fadd_rn(wo.y, wi.y), __fadd_rn(wo.z, wi.z));
     f3 h = safe_normalize(hsum);
-    float woDotH = dot(wo, h), nDotH = dot(nrm, h);
+    float woDotH = dot_exact(wo, h), nDotH = dot_exact(nrm, h);
     float D = fwd_ndf_ggx(alphaSqr, nDotH);
     float G = fwd_masking_smith(alphaSqr, woDotN, wiDotN);
     f3 F = fwd_fresnel3(col, F3(1.0f), woDotH);
@@ -193,7 +201,7 @@ __device__ __forceinline__ f3 spec_color(f3 kd, f3 arm) { return (F3(0.04f * (1.
 __device__ __forceinline__ void ox_fwd_pbr_bsdf(f3 kd, f3 arm, f3 wo, f3 nrm, f3 wi, float min_roughness, float &diffuse, f3 &specular)
 {
     diffuse = fwd_lambert(nrm, wi);
-    specular = fwd_pbr_specular(spec_color(kd, arm), nrm, wo, wi, arm.y * arm.y, min_roughness);
+    specular = fwd_pbr_specular(spec_color(kd, arm), nrm, wo, wi, __fmul_rn(arm.y, arm.y), min_roughness);
 }
 // d_wo is returned so the caller can push it through wo = normalize(view_pos - pos) once per pixel
 // (the map is linear in d_wo, so summing d_wo over samples first is exact up to rounding).
@@ -203,7 +211,7 @@ __device__ __forceinline__ void ox_bwd_pbr_bsdf(f3 kd, f3 arm, f3 wo, f3 nrm, f3
     f3 sc = spec_color(kd, arm);
     float d_alpha = 0.0f;
     f3 d_sc = F3(0.0f), d_wi = F3(0.0f);
-    bwd_pbr_specular(sc, nrm, wo, wi, arm.y * arm.y, min_roughness, d_sc, d_nrm, d_wo, d_wi, d_alpha, d_specular);
+    bwd_pbr_specular(sc, nrm, wo, wi, __fmul_rn(arm.y, arm.y), min_roughness, d_sc, d_nrm, d_wo, d_wi, d_alpha, d_specular);
     bwd_lambert(nrm, wi, d_nrm, d_wi, d_diffuse);
     d_kd -= d_sc * ((arm.x - 1.0f) * arm.z);
     d_arm.x += sum(d_sc * ((F3(0.04f) - kd) * arm.z - F3(0.04f)));
@@ -257,7 +265,7 @@ __device__ __forceinline__ f3 ru_fwd_pbr_bsdf(f3 kd, f3 arm, f3 pos, f3 nrm, f3 
     f3 wo = safe_normalize(view_pos - pos), wi = safe_normalize(light_pos - pos);
     float diff = BSDF == 0 ? fwd_lambert(nrm, wi) : fwd_frostbite(nrm, wi, wo, arm.y);
     f3 diffuse = kd * ((1.0f - arm.z) * diff);
-    return diffuse + fwd_pbr_specular(spec_color(kd, arm), nrm, wo, wi, arm.y * arm.y, min_roughness);
+    return diffuse + fwd_pbr_specular(spec_color(kd, arm), nrm, wo, wi, __fmul_rn(arm.y, arm.y), min_roughness);
 }
 __device__ __forceinline__ void ru_bwd_pbr_bsdf(f3 kd, f3 arm, f3 pos, f3 nrm, f3 view_pos, f3 light_pos, float min_roughness, int BSDF,
                                                 f3 &d_kd, f3 &d_arm, f3 &d_pos, f3 &d_nrm, f3 &d_view_pos, f3 &d_light_pos, f3 d_out)
@@ -269,7 +277,7 @@ __device__ __forceinline__ void ru_bwd_pbr_bsdf(f3 kd, f3 arm, f3 pos, f3 nrm, f
     float diff = BSDF == 0 ? fwd_lambert(nrm, wi) : fwd_frostbite(nrm, wi, wo, arm.y);
     float d_alpha = 0.0f;
     f3 d_sc = F3(0.0f), d_wi = F3(0.0f), d_wo = F3(0.0f);
-    bwd_pbr_specular(sc, nrm, wo, wi, arm.y * arm.y, min_roughness, d_sc, d_nrm, d_wo, d_wi, d_alpha, d_out);
+    bwd_pbr_specular(sc, nrm, wo, wi, __fmul_rn(arm.y, arm.y), min_roughness, d_sc, d_nrm, d_wo, d_wi, d_alpha, d_out);
     float d_diff = sum(diff_col * d_out);
     if (BSDF == 0) bwd_lambert(nrm, wi, d_nrm, d_wi, d_diff);
     else bwd_frostbite(nrm, wi, wo, arm.y, d_nrm, d_wi, d_wo, d_arm.y, d_diff);
