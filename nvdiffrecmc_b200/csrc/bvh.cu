@@ -121,7 +121,7 @@ __device__ __forceinline__ int lbvh_delta(const uint32_t *__restrict__ k, int n,
 
 // Karras 2012, "Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees"
 __global__ void __launch_bounds__(256) k_karras(const uint32_t *__restrict__ k, int T, int32_t *__restrict__ left, int32_t *__restrict__ right,
-                                                int32_t *__restrict__ parent)
+                                                int32_t *__restrict__ parent, int2 *__restrict__ range)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T - 1) return;
@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(256) k_karras(const uint32_t *__restrict__ k, 
     int rc = (hi_ == gamma + 1) ? (T - 1) + gamma + 1 : gamma + 1;
     left[i] = lc; right[i] = rc;
     parent[lc] = i; parent[rc] = i;
+    range[i] = make_int2(lo_, hi_);           // sorted-triangle range covered by this node
     if (i == 0) parent[0] = -1;
 }
 
@@ -200,16 +201,28 @@ __global__ void __launch_bounds__(256) k_leaves_refit(const float *__restrict__ 
     }
 }
 
+// Traversal nodes: node i holds the boxes of its two children.  A child whose subtree covers at most
+// MCS_LEAF_MAX triangles is emitted as a leaf run (the triangles of an LBVH subtree are consecutive in
+// Morton order); the internal nodes below it are simply never referenced.
+__device__ __forceinline__ int child_code(int c, int T, const int2 *__restrict__ range)
+{
+    if (c >= T - 1) return ~(((c - (T - 1)) << 3) | 0);
+    const int2 r = range[c];
+    const int cnt = r.y - r.x + 1;
+    return cnt <= MCS_LEAF_MAX ? ~((r.x << 3) | (cnt - 1)) : c;
+}
+
 __global__ void __launch_bounds__(256) k_emit_nodes(int T, const int32_t *__restrict__ left, const int32_t *__restrict__ right,
-                                                    const float *__restrict__ lo, const float *__restrict__ hi, float4 *__restrict__ nodes)
+                                                    const int2 *__restrict__ range, const float *__restrict__ lo, const float *__restrict__ hi,
+                                                    float4 *__restrict__ nodes)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (T == 1) {
-        if (i == 0) {   // single triangle: child 0 = the leaf, child 1 = an empty box
+    if (T <= MCS_LEAF_MAX) {
+        if (i == 0) {   // tiny mesh: the root is one leaf run; child 1 is an empty box (node 0 of lo/hi is the root box, or the only leaf)
             nodes[0] = make_float4(lo[0], hi[0], lo[1], hi[1]);
             nodes[1] = make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY);
             nodes[2] = make_float4(lo[2], hi[2], INFINITY, -INFINITY);
-            nodes[3] = make_float4(__int_as_float(~0), __int_as_float(~0), 0.0f, 0.0f);
+            nodes[3] = make_float4(__int_as_float(~((0 << 3) | (T - 1))), __int_as_float(~0), 0.0f, 0.0f);
         }
         return;
     }
@@ -219,9 +232,7 @@ __global__ void __launch_bounds__(256) k_emit_nodes(int T, const int32_t *__rest
     nodes[4 * (size_t)i + 0] = make_float4(l0[0], h0[0], l0[1], h0[1]);
     nodes[4 * (size_t)i + 1] = make_float4(l1[0], h1[0], l1[1], h1[1]);
     nodes[4 * (size_t)i + 2] = make_float4(l0[2], h0[2], l1[2], h1[2]);
-    int e0 = c0 >= T - 1 ? ~(c0 - (T - 1)) : c0;
-    int e1 = c1 >= T - 1 ? ~(c1 - (T - 1)) : c1;
-    nodes[4 * (size_t)i + 3] = make_float4(__int_as_float(e0), __int_as_float(e1), 0.0f, 0.0f);
+    nodes[4 * (size_t)i + 3] = make_float4(__int_as_float(child_code(c0, T, range)), __int_as_float(child_code(c1, T, range)), 0.0f, 0.0f);
 }
 
 __global__ void __launch_bounds__(128) k_visibility(BvhView b, const float *__restrict__ ro, const float *__restrict__ rd, int64_t n, uint8_t *__restrict__ vis)
@@ -264,7 +275,7 @@ int mcs_ctx_destroy(mcs_ctx *c)
 {
     if (!c) return 0;
     DevBuf *bufs[] = {&c->bounds, &c->tlo, &c->thi, &c->keys, &c->keys_alt, &c->vals, &c->vals_alt, &c->left, &c->right, &c->parent,
-                      &c->lo, &c->hi, &c->flags, &c->sort_tmp, &c->nodes, &c->tris, &c->lcg_skip, &c->light_grad4};
+                      &c->lo, &c->hi, &c->flags, &c->range, &c->sort_tmp, &c->nodes, &c->tris, &c->lcg_skip, &c->light_grad4};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     delete c;
@@ -293,6 +304,7 @@ int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris
     if (int e = mcs_buf_reserve(c->lo, nN * 3 * sizeof(float), s)) return e;
     if (int e = mcs_buf_reserve(c->hi, nN * 3 * sizeof(float), s)) return e;
     if (int e = mcs_buf_reserve(c->flags, nT * sizeof(int), s)) return e;
+    if (int e = mcs_buf_reserve(c->range, nT * sizeof(int2), s)) return e;
     if (int e = mcs_buf_reserve(c->nodes, nT * 4 * sizeof(float4), s)) return e;
     if (int e = mcs_buf_reserve(c->tris, nT * 3 * sizeof(float4), s)) return e;
 
@@ -311,7 +323,8 @@ int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris
         MCS_CUDA(cub::DeviceRadixSort::SortPairs(c->sort_tmp.p, tmp_bytes, (const uint32_t *)c->keys.p, (uint32_t *)c->keys_alt.p,
                                                  (const int32_t *)c->vals.p, (int32_t *)c->vals_alt.p, T, 0, 30, s));
         if (T > 1) {
-            k_karras<<<nblk(T - 1, 256), 256, 0, s>>>((const uint32_t *)c->keys_alt.p, T, (int32_t *)c->left.p, (int32_t *)c->right.p, (int32_t *)c->parent.p);
+            k_karras<<<nblk(T - 1, 256), 256, 0, s>>>((const uint32_t *)c->keys_alt.p, T, (int32_t *)c->left.p, (int32_t *)c->right.p, (int32_t *)c->parent.p,
+                                                      (int2 *)c->range.p);
             MCS_LAUNCH_CHECK();
         }
     }
@@ -320,8 +333,8 @@ int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris
                                                 (const int32_t *)c->right.p, (const int32_t *)c->parent.p, (float *)c->lo.p, (float *)c->hi.p,
                                                 (int *)c->flags.p, (float4 *)c->tris.p);
     MCS_LAUNCH_CHECK();
-    k_emit_nodes<<<nblk(T > 1 ? T - 1 : 1, 256), 256, 0, s>>>(T, (const int32_t *)c->left.p, (const int32_t *)c->right.p, (const float *)c->lo.p,
-                                                              (const float *)c->hi.p, (float4 *)c->nodes.p);
+    k_emit_nodes<<<nblk(T > 1 ? T - 1 : 1, 256), 256, 0, s>>>(T, (const int32_t *)c->left.p, (const int32_t *)c->right.p, (const int2 *)c->range.p,
+                                                              (const float *)c->lo.p, (const float *)c->hi.p, (float4 *)c->nodes.p);
     MCS_LAUNCH_CHECK();
     c->T = T; c->V = V;
     return 0;

@@ -3,7 +3,9 @@
 // Replaces optixTrace() (render/optixutils/c_src/envsampling/kernel.cu:101-118): B200 has no RT
 // cores, so visibility is a hand-written stack traversal of a binary BVH whose 64-byte nodes hold
 // BOTH children's boxes (one node visit = four 128-bit loads through the read-only path, then two
-// slab tests), with leaves of one triangle stored as three float4 (v0, e1, e2) in Morton order.
+// slab tests); a leaf is a run of up to MCS_LEAF_MAX consecutive triangles in Morton order (an LBVH
+// subtree collapsed at build time), each stored as three float4 (v0, e1, e2).  Child codes: >= 0 internal
+// node index, < 0 leaf with ~code = (first_triangle << 3) | (count - 1).
 //
 // Parity contract (DESIGN.md "visibility"): the boolean result equals the oracle's brute-force loop
 // bit for bit because (a) the triangle predicate mt_hit() is evaluated with the exact operation
@@ -58,6 +60,7 @@ __device__ __forceinline__ RayPre ray_pre(f3 o, f3 d)
 }
 
 #define MCS_STACK 64
+#define MCS_LEAF_MAX 4
 #define MCS_TMAX 1e16f
 
 // Any-hit query: true if some triangle is hit with t in (0, 1e16).
@@ -92,10 +95,14 @@ __device__ __forceinline__ bool bvh_occluded(const BvhView &b, f3 o, f3 d)
             if (h0) { node = ch0; continue; }
             if (h1) { node = ch1; continue; }
         } else {
-            const float4 *t = b.tris + 3 * (size_t)(~node);
-            const float4 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2);
-            float tt, uu, vv;
-            if (mt_hit(o, d, F3(t0.x, t0.y, t0.z), F3(t1.x, t1.y, t1.z), F3(t2.x, t2.y, t2.z), MCS_TMAX, tt, uu, vv)) return true;
+            const int code = ~node;
+            const int start = code >> 3, cnt = (code & 7) + 1;
+            for (int k = 0; k < cnt; ++k) {
+                const float4 *t = b.tris + 3 * (size_t)(start + k);
+                const float4 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2);
+                float tt, uu, vv;
+                if (mt_hit(o, d, F3(t0.x, t0.y, t0.z), F3(t1.x, t1.y, t1.z), F3(t2.x, t2.y, t2.z), MCS_TMAX, tt, uu, vv)) return true;
+            }
         }
         if (sp == 0) return false;
         node = stack[--sp];
@@ -137,13 +144,17 @@ __device__ __forceinline__ int bvh_closest(const BvhView &b, f3 o, f3 d, float &
             if (h0) { node = ch0; continue; }
             if (h1) { node = ch1; continue; }
         } else {
-            const float4 *t = b.tris + 3 * (size_t)(~node);
-            const float4 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2);
-            float tt, uu, vv;
-            // tmax slightly above t_best so exact ties are still seen and resolved by triangle id
-            if (mt_hit(o, d, F3(t0.x, t0.y, t0.z), F3(t1.x, t1.y, t1.z), F3(t2.x, t2.y, t2.z), MCS_TMAX, tt, uu, vv)) {
-                const int id = __float_as_int(t0.w);
-                if (tt < t_best || (tt == t_best && id < best)) { t_best = tt; u_best = uu; v_best = vv; best = id; }
+            const int code = ~node;
+            const int start = code >> 3, cnt = (code & 7) + 1;
+            for (int k = 0; k < cnt; ++k) {
+                const float4 *t = b.tris + 3 * (size_t)(start + k);
+                const float4 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2);
+                float tt, uu, vv;
+                // exact ties in t are resolved by the original triangle id (brute-force order)
+                if (mt_hit(o, d, F3(t0.x, t0.y, t0.z), F3(t1.x, t1.y, t1.z), F3(t2.x, t2.y, t2.z), MCS_TMAX, tt, uu, vv)) {
+                    const int id = __float_as_int(t0.w);
+                    if (tt < t_best || (tt == t_best && id < best)) { t_best = tt; u_best = uu; v_best = vv; best = id; }
+                }
             }
         }
         if (sp == 0) return best;

@@ -22,6 +22,7 @@ struct mcs_ctx {
     DevBuf left, right, parent;  // [T-1],[T-1],[2T-1]
     DevBuf lo, hi;               // [2T-1][3] padded node boxes
     DevBuf flags;                // [T-1] refit arrival counters
+    DevBuf range;                // [T-1] int2: sorted-triangle range of each internal node
     DevBuf sort_tmp;
     // ---- traversal layout ----
     DevBuf nodes;                // [max(T-1,1)] x 4 float4 (two child boxes + child codes)

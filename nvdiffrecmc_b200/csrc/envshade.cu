@@ -5,7 +5,15 @@
 // env_shade_bwd (render/optixutils/c_src/torch_bindings.cpp:123-272).
 //
 // B200 mapping (no RT cores, 148 SMs):
-//   * ONE WARP PER PIXEL, ONE LANE PER SAMPLE.  The reference runs one thread per pixel and loops
+//   * ONE WARP PER PIXEL GROUP, ONE LANE PER SAMPLE, THREE PHASES PER GROUP (v2, see profiles/r01_v1_*: the v1 kernel
+//     traced inline and ran its traversal loop at 10/32 active lanes):
+//       G  generate: all lanes draw samples (exact path), rays that can contribute (n.wi > 0) are compacted into a
+//          per-warp shared-memory queue (direction, env texel, MIS weight) -- up to 256 rays = 2 pixels at N=8;
+//       T  trace: while-while BVH traversal with dynamic fetch -- a lane that finishes pulls the next queued ray,
+//          so traversal runs with (nearly) full warps until the queue drains; the result is one bit per ray;
+//       E  evaluate: surviving rays (V != 0) are compacted again and only those evaluate the BSDF (forward) or its
+//          adjoint + the env-map gradient scatter (backward), then warp-shuffle reduction, one writer per pixel.
+//     The reference runs one thread per pixel and loops
 //     2*N^2 samples serially; here the 2*N^2 (stratum, sample-type) items of a pixel are spread over
 //     the 32 lanes (items [0,N^2) are light samples, [N^2,2N^2) BSDF samples, so a 32-item round is
 //     type-uniform whenever N^2 is a multiple of 32).  All rays of a warp share their origin, which
@@ -94,8 +102,6 @@ __device__ __forceinline__ xf sample_cdf(const float *__restrict__ cdf, int stri
     return xmin(sample / pdf, xf(0.99999994f));
 }
 
-struct Texel { int x, y; float sin_theta_arg; };
-
 // kernel.cu:124-129 + 177-178: direction -> lat-long coordinate -> nearest texel (decision path)
 __device__ __forceinline__ void dir_to_texel(const EnvParams &p, xf3 dir, int &tx, int &ty, float &cy)
 {
@@ -123,11 +129,12 @@ __device__ __forceinline__ float light_pdf_value(const EnvParams &p, int tx, int
 }
 
 // kernel.cu:217-237
+// (the denominator cancels catastrophically at the specular peak: exact order, see bsdf.cuh "conditioning note")
 __device__ __forceinline__ float eval_ndf_ggx(float alpha, float c)
 {
-    float a2 = alpha * alpha;
-    float d = (c * a2 - c) * c + 1.0f;
-    return a2 / (d * d * MCS_PI);
+    xf a2 = xf(alpha) * xf(alpha);
+    xf d = (xf(c) * a2 - xf(c)) * xf(c) + xf(1.0f);
+    return a2.v / ((d * d).v * MCS_PI);
 }
 __device__ __forceinline__ float eval_g1_ggx(float alphaSqr, float c)
 {
@@ -155,11 +162,12 @@ __device__ __forceinline__ xf3 x_toworld(xf3 a, const PixelFrame &f) { return f.
 // kernel.cu:301-323 (value path)
 __device__ __forceinline__ float ggx_pdf_value(const PixelFrame &f, f3 wi)
 {
-    f3 wo_l = toF3(f.wo_l_raw);
-    f3 wi_l = F3(dot(wi, toF3(f.U)), dot(wi, toF3(f.V)), dot(wi, toF3(f.W)));
+    const f3 wo_l = toF3(f.wo_l_raw);
+    const xf3 wi_lx = x_tolocal(X3(wi), f);
+    const f3 wi_l = toF3(wi_lx);
     float pdf = 0.0f;
     if (wo_l.z > 0.0f && wi_l.z > 0.0f) {
-        f3 m = safe_normalize(wi_l + wo_l);
+        const f3 m = toF3(xnormalize(wi_lx + f.wo_l_raw));
         float woDotH = dot(m, wo_l);
         float alpha = f.alpha.v;
         float D = eval_ndf_ggx(alpha, m.z);
@@ -241,18 +249,247 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Per-warp ray queue in shared memory (SoA, conflict-free: lane k touches word k of each array).
+// One "chunk" holds the live rays of up to MAX_PIX pixels (or a 256-item slice of one pixel when
+// 2*N^2 > 256).  tex bit 31 = "visible" flag written by the trace phase.
+// ---------------------------------------------------------------------------------------------
+constexpr int QCAP = 256;
+constexpr int MAX_PIX = 8;
+struct WarpQueue {
+    float dx[QCAP], dy[QCAP], dz[QCAP], mis[QCAP];
+    uint32_t tex[QCAP];
+    uint16_t vlist[QCAP];       // dense list of entries that reach the eval phase
+    uint16_t qpix[QCAP];        // pixel slot of the entry
+    float ro[MAX_PIX][3];
+    float wo[MAX_PIX][3];
+    int seg_end[MAX_PIX];
+    int pixid[MAX_PIX];         // linear pixel index of each slot
+};
+struct WarpQueueRec { uint32_t slot[QCAP]; };   // MODE 2 only
+
+struct PixelIn {
+    f3 ro, pos, nrm, view, kd, ks;
+    int ix, iy, iz;
+    int64_t pix;
+};
+
+__device__ __forceinline__ PixelIn load_pixel(const EnvParams &p, int64_t pix)
+{
+    PixelIn q;
+    q.pix = pix;
+    q.ix = (int)(pix % p.W);
+    const int64_t tt = pix / p.W;
+    q.iy = (int)(tt % p.H); q.iz = (int)(tt / p.H);
+    q.ro = p.ro.ld3(q.iz, q.iy, q.ix);
+    q.pos = p.pos.ld3(q.iz, q.iy, q.ix);
+    q.nrm = p.nrm.ld3(q.iz, q.iy, q.ix);
+    q.view = p.view.ld3(q.iz, q.iy, q.ix);
+    q.kd = p.kd.ld3(q.iz, q.iy, q.ix);
+    q.ks = p.ks.ld3(q.iz, q.iy, q.ix);
+    return q;
+}
+
+// kernel.cu:490-502: shading frame + lobe probabilities
+__device__ __forceinline__ void make_frame(const PixelIn &q, PixelFrame &f)
+{
+    f.N = X3(q.nrm);
+    f.alpha = xf(q.ks.y) * xf(q.ks.y);
+    f.wo = xnormalize(X3(q.view) - X3(q.pos));
+    xf metallic = xf(q.ks.z);
+    xf3 base = X3(q.kd);
+    xf om = xf(1.0f) - metallic;
+    xf3 specColor = X3(xf(0.04f) * om + base.x * metallic, xf(0.04f) * om + base.y * metallic, xf(0.04f) * om + base.z * metallic);
+    xf lum = base.x * xf(0.2126f) + base.y * xf(0.7152f) + base.z * xf(0.0722f);
+    xf diffuseWeight = om * lum;
+    // albedo(), kernel.cu:81-94
+    f.W = xnormalize(f.N);
+    xONB(f.W, f.U, f.V);
+    f.wo_l_raw = x_tolocal(f.wo, f);
+    f.wo_l = xnormalize(f.wo_l_raw);
+    xf specularWeight = xf(0.0f);
+    if (f.wo_l.z.v > 0.0f) {
+        xf c = xclamp(f.wo_l.z, xf(1e-4f), xf(1.0f) - xf(1e-4f));
+        xf o = xf(1.0f) - c;
+        xf o2 = o * o;
+        xf scale = (o2 * o2) * o;
+        xf os = xf(1.0f) - scale;
+        xf3 F = X3(specColor.x * os + scale, specColor.y * os + scale, specColor.z * os + scale);
+        specularWeight = F.x * xf(0.2126f) + F.y * xf(0.7152f) + F.z * xf(0.0722f);
+    }
+    xf sumw = diffuseWeight + specularWeight;
+    f.pDiffuse = sumw.v > 0.0f ? diffuseWeight / sumw : xf(1.0f);
+    f.pSpecular = xf(1.0f) - f.pDiffuse;
+    f.NdotV = xdot(f.N, f.wo);
+}
+
+// ---- phase G: generate the items [w0, w1) of one pixel, push the rays that can contribute ----------
+template <int MODE>
+__device__ __forceinline__ void gen_segment(const EnvParams &p, WarpQueue &q, WarpQueueRec *qr, const PixelIn &px, const PixelFrame &f,
+                                            int slot, int w0, int w1, int &qn, const int lane)
+{
+    const int S = p.S;
+    const xf strata_frac = xf(1.0f) / xf((float)(unsigned)p.N);
+    // RNG, kernel.cu:504-505
+    uint32_t s_seed = p.seed, s_pix = (uint32_t)(((px.iz + p.batch_offset) * p.H + px.iy) * p.W + px.ix);
+    uint32_t rng = rand_pcg(s_seed) ^ rand_pcg(s_pix);
+    const uint32_t lightIdx = rand_pcg(rng) % p.n_perms;
+    const uint32_t bsdfIdx = rand_pcg(rng) % p.n_perms;
+    const uint32_t rng2 = rng;
+    const f3 nrm = px.nrm;
+
+    for (int base = w0; base < w1; base += 32) {
+        const int w = base + lane;
+        const bool valid = w < w1;
+        const bool is_bsdf = w >= S;
+        const int i = is_bsdf ? w - S : w;
+        xf3 dir = X3(xf(0.0f), xf(0.0f), xf(1.0f));
+        float pdf_sum = 1.0f;
+        int tx = 0, ty = 0;
+        if (valid) {
+            const uint2 sk = __ldg(p.skip + 5 * i + (is_bsdf ? 2 : 0));
+            uint32_t st = rng2 * sk.x + sk.y;
+            const uint32_t row = is_bsdf ? bsdfIdx : lightIdx;
+            const uint32_t perm = (uint32_t)__ldg(p.perms + (size_t)row * p.pm_s1 + (size_t)i * p.pm_s3);
+            const xf sx = (xf((float)(perm % (uint32_t)p.N)) + uniform_pcg(st)) * strata_frac;
+            const xf sy = (xf((float)(perm / (uint32_t)p.N)) + uniform_pcg(st)) * strata_frac;
+            float cy;
+            if (!is_bsdf) {
+                // lightSample, kernel.cu:184-193
+                uint32_t cyi, cxi;
+                xf ry = sample_cdf(p.rows, p.r_s, p.Hl, p.m_rows, sy, cyi);
+                xf rx = sample_cdf(p.cols + (size_t)cyi * p.c_s1, p.c_s2, p.Wl, p.m_cols, sx, cxi);
+                dir = tc_to_dir((xf((float)cxi) + rx) / xf((float)p.Wl), (xf((float)cyi) + ry) / xf((float)p.Hl));
+                dir_to_texel(p, dir, tx, ty, cy);
+                pdf_sum = light_pdf_value(p, tx, ty, cy) + bsdf_pdf_value(f, dir);
+            } else {
+                const xf sz = uniform_pcg(st);
+                float pdf_b;
+                dir = bsdf_sample(f, sx, sy, sz, pdf_b);
+                dir_to_texel(p, dir, tx, ty, cy);
+                pdf_sum = light_pdf_value(p, tx, ty, cy) + pdf_b;
+            }
+        }
+        const f3 wi = toF3(dir);
+        // A sample contributes (value and every adjoint) only if n.wi > 0: Lambert is max(n.wi/pi, 0) and the GGX lobe is gated by
+        // wiDotN > 1e-4 (bsdf.h:21-30,160,186); everything else is multiplied by those.  Such rays are neither traced nor evaluated.
+        const bool live = valid && dot(nrm, wi) > 0.0f;
+        if (MODE == 2 && valid) {
+            const size_t rec = (size_t)px.pix * (2 * S) + (size_t)(2 * i + (is_bsdf ? 1 : 0));
+            p.rec_texel[rec] = (ty << 16) | tx;
+            if (!live) p.rec_vis[rec] = 2;
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+        if (live) {
+            const int e = qn + __popc(m & ((1u << lane) - 1u));
+            q.dx[e] = wi.x; q.dy[e] = wi.y; q.dz[e] = wi.z;
+            q.mis[e] = 1.0f / fmaxf(pdf_sum, 0.0001f);          // MIS balance heuristic, kernel.cu:409
+            q.tex[e] = (uint32_t)((ty << 16) | tx);
+            q.qpix[e] = (uint16_t)slot;
+            if (MODE == 2) qr->slot[e] = (uint32_t)(2 * i + (is_bsdf ? 1 : 0));
+        }
+        qn += __popc(m);
+    }
+}
+
+// ---- phase T: any-hit traversal of all queued rays with dynamic ray fetch -------------------------
+// while-while traversal (Aila & Laine): lanes walk internal nodes until they reach a leaf or finish, then
+// test leaf triangles; a lane that finishes its ray pulls the next one from the warp queue as soon as fewer
+// than REFILL_BELOW lanes are busy, so the warp stays populated until the queue drains.
+__device__ __forceinline__ void trace_queue(const EnvParams &p, WarpQueue &q, const int qn, const int lane)
+{
+    constexpr int REFILL_BELOW = 24;
+    constexpr int DONE = 0x7FFFFFFF;
+    int head = 0;
+    int my = -1;
+    int node = DONE, sp = 0;
+    int stack[MCS_STACK];
+    f3 o = F3(0.0f), d = F3(0.0f);
+    RayPre r = ray_pre(F3(0.0f), F3(1.0f));
+    const BvhView b = p.bvh;
+    while (true) {
+        // refill idle lanes
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, my < 0);
+        if (idle && head < qn) {
+            const int idx = head + __popc(idle & ((1u << lane) - 1u));
+            if (my < 0 && idx < qn) {
+                my = idx;
+                const int ps = q.qpix[idx];
+                o = F3(q.ro[ps][0], q.ro[ps][1], q.ro[ps][2]);
+                d = F3(q.dx[idx], q.dy[idx], q.dz[idx]);
+                r = ray_pre(o, d);
+                node = 0; sp = 0;
+            }
+            head += __popc(idle);
+        }
+        if (__ballot_sync(0xFFFFFFFFu, my >= 0) == 0u) break;
+        const int thresh = head < qn ? REFILL_BELOW : 1;
+        do {
+            // internal nodes
+            while (node >= 0 && node != DONE) {
+                const float4 *n = b.nodes + 4 * (size_t)node;
+                const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
+                float a0 = fmaf(q0.x, r.ix, -r.ox), a1 = fmaf(q0.y, r.ix, -r.ox);
+                float b0 = fmaf(q0.z, r.iy, -r.oy), b1 = fmaf(q0.w, r.iy, -r.oy);
+                float c0 = fmaf(q2.x, r.iz, -r.oz), c1 = fmaf(q2.y, r.iz, -r.oz);
+                const float tn0 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
+                const float tf0 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), MCS_TMAX));
+                a0 = fmaf(q1.x, r.ix, -r.ox); a1 = fmaf(q1.y, r.ix, -r.ox);
+                b0 = fmaf(q1.z, r.iy, -r.oy); b1 = fmaf(q1.w, r.iy, -r.oy);
+                c0 = fmaf(q2.z, r.iz, -r.oz); c1 = fmaf(q2.w, r.iz, -r.oz);
+                const float tn1 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
+                const float tf1 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), MCS_TMAX));
+                const bool h0 = tn0 <= tf0 * 1.0000004f, h1 = tn1 <= tf1 * 1.0000004f;
+                const int ch0 = __float_as_int(q3.x), ch1 = __float_as_int(q3.y);
+                if (h0 && h1) {
+                    const bool first0 = tn0 <= tn1;
+                    stack[sp++] = first0 ? ch1 : ch0;
+                    node = first0 ? ch0 : ch1;
+                } else if (h0) node = ch0;
+                else if (h1) node = ch1;
+                else node = sp ? stack[--sp] : DONE;
+            }
+            // leaf: a run of consecutive triangles in Morton order
+            if (node < 0) {
+                const int code = ~node;
+                const int start = code >> 3, cnt = (code & 7) + 1;
+                bool hit = false;
+                for (int k = 0; k < cnt && !hit; ++k) {
+                    const float4 *t = b.tris + 3 * (size_t)(start + k);
+                    const float4 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2);
+                    float tt, uu, vv;
+                    hit = mt_hit(o, d, F3(t0.x, t0.y, t0.z), F3(t1.x, t1.y, t1.z), F3(t2.x, t2.y, t2.z), MCS_TMAX, tt, uu, vv);
+                }
+                if (hit) { node = DONE; sp = -1; }            // occluded
+                else node = sp ? stack[--sp] : DONE;
+            }
+            if (node == DONE && my >= 0) {
+                if (sp == 0) q.tex[my] |= 0x80000000u;        // stack ran empty without a hit: visible
+                my = -1;
+            }
+        } while ((int)__popc(__ballot_sync(0xFFFFFFFFu, my >= 0)) >= thresh);
+    }
+    __syncwarp();
+}
+
 // MODE 0: forward, 1: backward, 2: forward + per-ray records
 template <int MODE>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) env_shade_kernel(const EnvParams p)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) env_shade_kernel(const EnvParams p)
 {
-    const int lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpQueue &q = reinterpret_cast<WarpQueue *>(smem_raw)[warp];
+    WarpQueueRec *qr = MODE == 2 ? reinterpret_cast<WarpQueueRec *>(smem_raw + sizeof(WarpQueue) * WARPS_PER_CTA) + warp : nullptr;
+
     const int64_t npix = (int64_t)p.B * p.H * p.W;
     const unsigned int nchunks = (unsigned int)((npix + 31) / 32);
     const int S = p.S, items = 2 * S;
-    const xf strata_frac = xf(1.0f) / xf((float)(unsigned)p.N);
     const float sample_frac = (xf(1.0f) / xf((float)(unsigned)(p.N * p.N))).v;
     const bool diffuse_only = (p.bsdf == 1u || p.bsdf == 2u);
     const bool trace_needed = p.shadow_scale != 0.0f;
+    const float v_occluded = 1.0f - p.shadow_scale;          // V of an occluded ray (kernel.cu:420)
+    // pixels whose rays are traced together
+    const int group = items <= QCAP ? min(MAX_PIX, QCAP / items) : 1;
 
     while (true) {
         unsigned int chunk = 0;
@@ -261,14 +498,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) env_shade_kernel(const Env
         if (chunk >= nchunks) break;
 
         const int64_t mypix = (int64_t)chunk * 32 + lane;
-        int mz = 0, my = 0, mx = 0;
         bool mine = mypix < npix;
         float mval = 0.0f;
         if (mine) {
-            mx = (int)(mypix % p.W); int64_t t = mypix / p.W; my = (int)(t % p.H); mz = (int)(t / p.H);
-            mval = p.mask.ld1(mz, my, mx);
+            const int mx = (int)(mypix % p.W); const int64_t t = mypix / p.W;
+            mval = p.mask.ld1((int)(t / p.H), (int)(t % p.H), mx);
         }
-        const unsigned active = __ballot_sync(0xFFFFFFFFu, mine && mval > 0.0f);
+        unsigned rem = __ballot_sync(0xFFFFFFFFu, mine && mval > 0.0f);
         if (mine && !(mval > 0.0f)) {
             // masked pixel: outputs are zero (the reference returns early on zero-initialised tensors, kernel.cu:478)
             if (MODE != 1) {
@@ -280,176 +516,134 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) env_shade_kernel(const Env
             }
         }
 
-        unsigned rem = active;
         while (rem) {
-            const int src = __ffs(rem) - 1;
-            rem &= rem - 1;
-            const int64_t pix = (int64_t)chunk * 32 + src;
-            const int ix = (int)(pix % p.W);
-            const int64_t tt = pix / p.W;
-            const int iy = (int)(tt % p.H), iz = (int)(tt / p.H);
-
-            // ---- per-pixel record (broadcast loads) and shading frame ----
-            const f3 ro = p.ro.ld3(iz, iy, ix);
-            const f3 pos = p.pos.ld3(iz, iy, ix);
-            const f3 nrm = p.nrm.ld3(iz, iy, ix);
-            const f3 view = p.view.ld3(iz, iy, ix);
-            const f3 kd = p.kd.ld3(iz, iy, ix);
-            const f3 ks = p.ks.ld3(iz, iy, ix);
-
-            PixelFrame f;
-            f.N = X3(nrm);
-            f.alpha = xf(ks.y) * xf(ks.y);
-            f.wo = xnormalize(X3(view) - X3(pos));
-            {
-                xf metallic = xf(ks.z);
-                xf3 base = X3(kd);
-                xf om = xf(1.0f) - metallic;
-                xf3 specColor = X3(xf(0.04f) * om + base.x * metallic, xf(0.04f) * om + base.y * metallic, xf(0.04f) * om + base.z * metallic);
-                xf lum = base.x * xf(0.2126f) + base.y * xf(0.7152f) + base.z * xf(0.0722f);
-                xf diffuseWeight = om * lum;
-                // albedo(), kernel.cu:81-94
-                f.W = xnormalize(f.N);
-                xONB(f.W, f.U, f.V);
-                f.wo_l_raw = x_tolocal(f.wo, f);
-                f.wo_l = xnormalize(f.wo_l_raw);
-                xf specularWeight = xf(0.0f);
-                if (f.wo_l.z.v > 0.0f) {
-                    xf c = xclamp(f.wo_l.z, xf(1e-4f), xf(1.0f) - xf(1e-4f));
-                    xf o = xf(1.0f) - c;
-                    xf o2 = o * o;
-                    xf scale = (o2 * o2) * o;
-                    xf os = xf(1.0f) - scale;
-                    xf3 F = X3(specColor.x * os + scale, specColor.y * os + scale, specColor.z * os + scale);
-                    specularWeight = F.x * xf(0.2126f) + F.y * xf(0.7152f) + F.z * xf(0.0722f);
-                }
-                xf sumw = diffuseWeight + specularWeight;
-                f.pDiffuse = sumw.v > 0.0f ? diffuseWeight / sumw : xf(1.0f);
-                f.pSpecular = xf(1.0f) - f.pDiffuse;
-                f.NdotV = xdot(f.N, f.wo);
+            // ---- take up to `group` active pixels of this chunk ----
+            int npx = 0;
+            __syncwarp();
+            while (npx < group && rem) {
+                const int src = __ffs(rem) - 1;
+                rem &= rem - 1;
+                if (lane == 0) q.pixid[npx] = (int)((int64_t)chunk * 32 + src);
+                ++npx;
             }
-            const f3 wo_f = toF3(f.wo);
+            __syncwarp();
 
-            f3 dgrad = F3(0.0f), sgrad = F3(0.0f);
-            if (MODE == 1) { dgrad = p.diff_grad.ld3(iz, iy, ix); sgrad = p.spec_grad.ld3(iz, iy, ix); }
+            // accumulators: only used across sub-chunks when one pixel needs several queue fills (items > QCAP)
+            f3 accD = F3(0.0f), accS = F3(0.0f);
+            f3 g_kd = F3(0.0f), g_ks = F3(0.0f), g_nrm = F3(0.0f), g_wo = F3(0.0f);
 
-            // RNG, kernel.cu:504-505
-            uint32_t s_seed = p.seed, s_pix = (uint32_t)(((iz + p.batch_offset) * p.H + iy) * p.W + ix);
-            uint32_t rng = rand_pcg(s_seed) ^ rand_pcg(s_pix);
-            const uint32_t lightIdx = rand_pcg(rng) % p.n_perms;
-            const uint32_t bsdfIdx = rand_pcg(rng) % p.n_perms;
-            const uint32_t rng2 = rng;
-
-            f3 accD = F3(0.0f), accS = F3(0.0f);                       // fwd accumulators
-            f3 g_kd = F3(0.0f), g_ks = F3(0.0f), g_nrm = F3(0.0f), g_wo = F3(0.0f);   // bwd accumulators
-
-            for (int base = 0; base < items; base += 32) {
-                const int w = base + lane;
-                const bool valid = w < items;
-                const bool is_bsdf = w >= S;
-                const int i = is_bsdf ? w - S : w;
-
-                xf3 dir = X3(xf(0.0f), xf(0.0f), xf(1.0f));
-                float pdf_sum = 1.0f;
-                int tx = 0, ty = 0;
-                if (valid) {
-                    const uint2 sk = __ldg(p.skip + 5 * i + (is_bsdf ? 2 : 0));
-                    uint32_t st = rng2 * sk.x + sk.y;
-                    const uint32_t row = is_bsdf ? bsdfIdx : lightIdx;
-                    const uint32_t perm = (uint32_t)__ldg(p.perms + (size_t)row * p.pm_s1 + (size_t)i * p.pm_s3);
-                    const xf sx = (xf((float)(perm % (uint32_t)p.N)) + uniform_pcg(st)) * strata_frac;
-                    const xf sy = (xf((float)(perm / (uint32_t)p.N)) + uniform_pcg(st)) * strata_frac;
-                    float cy;
-                    if (!is_bsdf) {
-                        // lightSample, kernel.cu:184-193
-                        uint32_t cyi, cxi;
-                        xf ry = sample_cdf(p.rows, p.r_s, p.Hl, p.m_rows, sy, cyi);
-                        xf rx = sample_cdf(p.cols + (size_t)cyi * p.c_s1, p.c_s2, p.Wl, p.m_cols, sx, cxi);
-                        dir = tc_to_dir((xf((float)cxi) + rx) / xf((float)p.Wl), (xf((float)cyi) + ry) / xf((float)p.Hl));
-                        dir_to_texel(p, dir, tx, ty, cy);
-                        const float pdf_light = light_pdf_value(p, tx, ty, cy);
-                        const float pdf_b = bsdf_pdf_value(f, dir);
-                        pdf_sum = pdf_light + pdf_b;
-                    } else {
-                        const xf sz = uniform_pcg(st);
-                        float pdf_b;
-                        dir = bsdf_sample(f, sx, sy, sz, pdf_b);
-                        dir_to_texel(p, dir, tx, ty, cy);
-                        pdf_sum = light_pdf_value(p, tx, ty, cy) + pdf_b;
+            const int nsub = items <= QCAP ? 1 : (items + QCAP - 1) / QCAP;
+            for (int sub = 0; sub < nsub; ++sub) {
+                const int w0 = sub * QCAP, w1 = min(items, w0 + QCAP);
+                // ================= phase G =================
+                int qn = 0;
+                __syncwarp();
+#pragma unroll 1
+                for (int j = 0; j < npx; ++j) {
+                    const PixelIn px = load_pixel(p, (int64_t)q.pixid[j]);
+                    PixelFrame f;
+                    make_frame(px, f);
+                    if (lane < 3) {
+                        q.ro[j][lane] = lane == 0 ? px.ro.x : (lane == 1 ? px.ro.y : px.ro.z);
+                        q.wo[j][lane] = lane == 0 ? f.wo.x.v : (lane == 1 ? f.wo.y.v : f.wo.z.v);
+                    }
+                    gen_segment<MODE>(p, q, qr, px, f, j, w0, w1, qn, lane);
+                    if (lane == 0) q.seg_end[j] = qn;
+                }
+                __syncwarp();
+                // ================= phase T =================
+                if (trace_needed) trace_queue(p, q, qn, lane);
+                else {
+                    for (int e = lane; e < qn; e += 32) q.tex[e] |= 0x80000000u;
+                    __syncwarp();
+                }
+                if (MODE == 2) {
+                    for (int e = lane; e < qn; e += 32) {
+                        const size_t rec = (size_t)q.pixid[q.qpix[e]] * items + qr->slot[e];
+                        p.rec_vis[rec] = trace_needed ? (uint8_t)(q.tex[e] >> 31) : (uint8_t)2;
                     }
                 }
-
-                // process_sample, kernel.cu:403-461
-                const f3 wi = toF3(dir);
-                f3 light_col = F3(0.0f);
-                float diffv = 0.0f; f3 specv = F3(0.0f);
-                bool contributes = false;
-                if (valid) {
-                    const float *lp = p.light + (size_t)ty * p.l_s1 + (size_t)tx * p.l_s2;
-                    light_col = F3(__ldg(lp), __ldg(lp + p.l_s3), __ldg(lp + 2 * p.l_s3));
-                    if (diffuse_only) diffv = fwd_lambert(nrm, wi);
-                    else ox_fwd_pbr_bsdf(kd, ks, wo_f, nrm, wi, MIN_ROUGHNESS, diffv, specv);
-                    contributes = (diffv != 0.0f) || (specv.x != 0.0f) || (specv.y != 0.0f) || (specv.z != 0.0f);
-                }
-                const float mis = 1.0f / fmaxf(pdf_sum, 0.0001f);
-
-                bool visible = true;
-                const bool traced = valid && contributes && trace_needed;
-                if (traced) visible = !bvh_occluded(p.bvh, ro, wi);
-                const float Vv = (visible ? 1.0f : 0.0f) * p.shadow_scale + (1.0f - p.shadow_scale);
-
-                if (MODE == 2 && valid) {
-                    const size_t rec = (size_t)pix * items + (size_t)(2 * i + (is_bsdf ? 1 : 0));
-                    p.rec_texel[rec] = (ty << 16) | tx;
-                    p.rec_vis[rec] = traced ? (visible ? 1 : 0) : 2;
-                }
-
-                const float wgt = Vv * mis * sample_frac;
-                if (MODE != 1) {
-                    if (valid && contributes) {
-                        accD += light_col * (diffv * wgt);
-                        accS += specv * light_col * wgt;
+                // ================= phase E =================
+#pragma unroll 1
+                for (int j = 0; j < npx; ++j) {
+                    const int s0 = j ? q.seg_end[j - 1] : 0, s1 = q.seg_end[j];
+                    // dense list of entries with V != 0 (deterministic order)
+                    int vn = 0;
+                    for (int e0 = s0; e0 < s1; e0 += 32) {
+                        const int e = e0 + lane;
+                        const bool keep = e < s1 && ((q.tex[e] >> 31) || v_occluded != 0.0f);
+                        const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+                        if (keep) q.vlist[s0 + vn + __popc(m & ((1u << lane) - 1u))] = (uint16_t)e;
+                        vn += __popc(m);
                     }
-                } else if (valid && contributes && wgt != 0.0f) {
-                    // light gradient, kernel.cu:424-425 / 203-211
-                    const f3 lg = (dgrad * diffv + sgrad * specv) * wgt;
-                    float *gp = p.light_grad + ((size_t)ty * p.Wl + tx) * 3;
-                    if (lg.x != 0.0f) atomicAdd(gp, lg.x);
-                    if (lg.y != 0.0f) atomicAdd(gp + 1, lg.y);
-                    if (lg.z != 0.0f) atomicAdd(gp + 2, lg.z);
-                    const f3 dD = dgrad * light_col * wgt, dS = sgrad * light_col * wgt;
-                    if (diffuse_only) {
-                        f3 wi_grad = F3(0.0f);
-                        bwd_lambert(nrm, wi, g_nrm, wi_grad, sum(dD));
-                    } else {
-                        ox_bwd_pbr_bsdf(kd, ks, wo_f, nrm, wi, MIN_ROUGHNESS, g_kd, g_ks, g_wo, g_nrm, sum(dD), dS);
+                    __syncwarp();
+                    const PixelIn px = load_pixel(p, (int64_t)q.pixid[j]);
+                    const f3 wo_f = F3(q.wo[j][0], q.wo[j][1], q.wo[j][2]);
+                    f3 dgrad = F3(0.0f), sgrad = F3(0.0f);
+                    if (MODE == 1) { dgrad = p.diff_grad.ld3(px.iz, px.iy, px.ix); sgrad = p.spec_grad.ld3(px.iz, px.iy, px.ix); }
+                    if (nsub == 1) { accD = F3(0.0f); accS = F3(0.0f); g_kd = F3(0.0f); g_ks = F3(0.0f); g_nrm = F3(0.0f); g_wo = F3(0.0f); }
+
+                    for (int k = lane; k < vn; k += 32) {
+                        const int e = q.vlist[s0 + k];
+                        const f3 wi = F3(q.dx[e], q.dy[e], q.dz[e]);
+                        const uint32_t tex = q.tex[e];
+                        const int tx = tex & 0xFFFFu, ty = (tex >> 16) & 0x7FFFu;
+                        const float Vv = (tex >> 31) ? 1.0f : v_occluded;
+                        const float wgt = Vv * q.mis[e] * sample_frac;
+                        // process_sample, kernel.cu:403-461
+                        const float *lp = p.light + (size_t)ty * p.l_s1 + (size_t)tx * p.l_s2;
+                        const f3 light_col = F3(__ldg(lp), __ldg(lp + p.l_s3), __ldg(lp + 2 * p.l_s3));
+                        float diffv = 0.0f; f3 specv = F3(0.0f);
+                        if (diffuse_only) diffv = fwd_lambert(px.nrm, wi);
+                        else ox_fwd_pbr_bsdf(px.kd, px.ks, wo_f, px.nrm, wi, MIN_ROUGHNESS, diffv, specv);
+                        if (MODE != 1) {
+                            accD += light_col * (diffv * wgt);
+                            accS += specv * light_col * wgt;
+                        } else {
+                            // light gradient, kernel.cu:424-425 / 203-211
+                            const f3 lg = (dgrad * diffv + sgrad * specv) * wgt;
+                            float *gp = p.light_grad + ((size_t)ty * p.Wl + tx) * 3;
+                            if (lg.x != 0.0f) atomicAdd(gp, lg.x);
+                            if (lg.y != 0.0f) atomicAdd(gp + 1, lg.y);
+                            if (lg.z != 0.0f) atomicAdd(gp + 2, lg.z);
+                            const f3 dD = dgrad * light_col * wgt, dS = sgrad * light_col * wgt;
+                            if (diffuse_only) {
+                                f3 wi_grad = F3(0.0f);
+                                bwd_lambert(px.nrm, wi, g_nrm, wi_grad, sum(dD));
+                            } else {
+                                ox_bwd_pbr_bsdf(px.kd, px.ks, wo_f, px.nrm, wi, MIN_ROUGHNESS, g_kd, g_ks, g_wo, g_nrm, sum(dD), dS);
+                            }
+                        }
+                    }
+
+                    // ---- warp reduction, single writer per pixel (kernel.cu:442-456, 533-541) ----
+                    if (sub == nsub - 1) {
+                        if (MODE != 1) {
+                            float r0 = warp_sum(accD.x), r1 = warp_sum(accD.y), r2 = warp_sum(accD.z);
+                            float r3 = warp_sum(accS.x), r4 = warp_sum(accS.y), r5 = warp_sum(accS.z);
+                            if (lane == 0) {
+                                float *d = p.diff + px.pix * 3, *s = p.spec + px.pix * 3;
+                                d[0] = r0; d[1] = r1; d[2] = r2; s[0] = r3; s[1] = r4; s[2] = r5;
+                            }
+                        } else {
+                            f3 t_kd = F3(warp_sum(g_kd.x), warp_sum(g_kd.y), warp_sum(g_kd.z));
+                            f3 t_ks = F3(warp_sum(g_ks.x), warp_sum(g_ks.y), warp_sum(g_ks.z));
+                            f3 t_nrm = F3(warp_sum(g_nrm.x), warp_sum(g_nrm.y), warp_sum(g_nrm.z));
+                            f3 t_wo = F3(warp_sum(g_wo.x), warp_sum(g_wo.y), warp_sum(g_wo.z));
+                            if (lane == 0) {
+                                // wo = normalize(view_pos - pos): d_pos = -J^T d_wo (bsdf.h:270-274; d_view_pos is dropped, ops.py:105)
+                                f3 d__wo = F3(0.0f);
+                                bwd_safe_normalize(px.view - px.pos, d__wo, t_wo);
+                                float *a = p.pos_grad + px.pix * 3, *b = p.nrm_grad + px.pix * 3, *c = p.kd_grad + px.pix * 3, *d = p.ks_grad + px.pix * 3;
+                                a[0] = -d__wo.x; a[1] = -d__wo.y; a[2] = -d__wo.z;
+                                b[0] = t_nrm.x; b[1] = t_nrm.y; b[2] = t_nrm.z;
+                                c[0] = t_kd.x; c[1] = t_kd.y; c[2] = t_kd.z;
+                                d[0] = t_ks.x; d[1] = t_ks.y; d[2] = t_ks.z;
+                            }
+                        }
                     }
                 }
-            }
-
-            // ---- warp reduction, single writer per pixel ----
-            if (MODE != 1) {
-                float r0 = warp_sum(accD.x), r1 = warp_sum(accD.y), r2 = warp_sum(accD.z);
-                float r3 = warp_sum(accS.x), r4 = warp_sum(accS.y), r5 = warp_sum(accS.z);
-                if (lane == 0) {
-                    float *d = p.diff + pix * 3, *s = p.spec + pix * 3;
-                    d[0] = r0; d[1] = r1; d[2] = r2; s[0] = r3; s[1] = r4; s[2] = r5;
-                }
-            } else {
-                f3 t_kd = F3(warp_sum(g_kd.x), warp_sum(g_kd.y), warp_sum(g_kd.z));
-                f3 t_ks = F3(warp_sum(g_ks.x), warp_sum(g_ks.y), warp_sum(g_ks.z));
-                f3 t_nrm = F3(warp_sum(g_nrm.x), warp_sum(g_nrm.y), warp_sum(g_nrm.z));
-                f3 t_wo = F3(warp_sum(g_wo.x), warp_sum(g_wo.y), warp_sum(g_wo.z));
-                if (lane == 0) {
-                    // wo = normalize(view_pos - pos): d_pos = -J^T d_wo (bsdf.h:270-274; d_view_pos is dropped, ops.py:105)
-                    f3 d__wo = F3(0.0f);
-                    bwd_safe_normalize(view - pos, d__wo, t_wo);
-                    float *a = p.pos_grad + pix * 3, *b = p.nrm_grad + pix * 3, *c = p.kd_grad + pix * 3, *d = p.ks_grad + pix * 3;
-                    a[0] = -d__wo.x; a[1] = -d__wo.y; a[2] = -d__wo.z;
-                    b[0] = t_nrm.x; b[1] = t_nrm.y; b[2] = t_nrm.z;
-                    c[0] = t_kd.x; c[1] = t_kd.y; c[2] = t_kd.z;
-                    d[0] = t_ks.x; d[1] = t_ks.y; d[2] = t_ks.z;
-                }
+                __syncwarp();
             }
         }
     }
@@ -535,13 +729,15 @@ static int launch_env(const EnvParams &p, cudaStream_t s)
     int dev = 0, sms = 0, per_sm = 0;
     MCS_CUDA(cudaGetDevice(&dev));
     MCS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    MCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, env_shade_kernel<MODE>, WARPS_PER_CTA * 32, 0));
+    const size_t smem = (sizeof(WarpQueue) + (MODE == 2 ? sizeof(WarpQueueRec) : 0)) * WARPS_PER_CTA;
+    MCS_CUDA(cudaFuncSetAttribute(env_shade_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, env_shade_kernel<MODE>, WARPS_PER_CTA * 32, smem));
     if (per_sm < 1) per_sm = 1;
     const int64_t npix = (int64_t)p.B * p.H * p.W;
     int64_t want = (npix + 32 * WARPS_PER_CTA - 1) / (32 * WARPS_PER_CTA);
     int grid = (int)(want < (int64_t)sms * per_sm ? want : (int64_t)sms * per_sm);
     if (grid < 1) grid = 1;
-    env_shade_kernel<MODE><<<grid, WARPS_PER_CTA * 32, 0, s>>>(p);
+    env_shade_kernel<MODE><<<grid, WARPS_PER_CTA * 32, smem, s>>>(p);
     MCS_LAUNCH_CHECK();
     return 0;
 }
