@@ -42,6 +42,9 @@
 
 namespace {
 
+#ifndef MCS_ENV_OCC
+#define MCS_ENV_OCC 4
+#endif
 constexpr int WARPS_PER_CTA = 8;
 constexpr float MIN_ROUGHNESS = 0.08f;     // kernel.cu:17
 
@@ -474,7 +477,7 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, WarpQueue &q, co
 
 // MODE 0: forward, 1: backward, 2: forward + per-ray records
 template <int MODE>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) env_shade_kernel(const EnvParams p)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MCS_ENV_OCC) env_shade_kernel(const EnvParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
