@@ -65,6 +65,7 @@ def _envshade_struct(real):
             ("pos_grad", C.c_void_p), ("nrm_grad", C.c_void_p), ("kd_grad", C.c_void_p), ("ks_grad", C.c_void_p),
             ("light_grad", C.c_void_p),
             ("rec_texel", C.c_void_p), ("rec_vis", C.c_void_p), ("counters", C.c_void_p),
+            ("s_pos", C.c_void_p), ("s_nrm", C.c_void_p), ("s_kd", C.c_void_p), ("s_ks", C.c_void_p),
         ]
     return S
 
@@ -242,10 +243,11 @@ class Oracle:
     # ------------------------------------------------------------------ env shade
     def env_shade(self, scene, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms,
                   BSDF="pbr", n_samples_x=8, rnd_seed=0, shadow_scale=1.0, batch_offset=0, vis_mode="brute",
-                  grads=None, records=False, counters=False, parallel_bwd=False):
+                  grads=None, records=False, counters=False, parallel_bwd=False, sampling_gbuffer=None):
         """Forward (grads=None) -> (diff, spec[, records][, counters]);
         backward (grads=(diff_grad, spec_grad)) -> (pos_grad, nrm_grad, kd_grad, ks_grad, light_grad).
         Mirrors env_shade_fwd / env_shade_bwd, render/optixutils/c_src/torch_bindings.cpp:123-272."""
+        assert scene is None or scene.orc is self, "scene was built by a different Oracle instance (fp32 vs fp64 layouts differ)"
         ro = np.asarray(ro, self.dt)
         B, H, W = ro.shape[:3]
         full = (B, H, W, 3)
@@ -270,6 +272,10 @@ class Oracle:
         p.mask, p.ro, p.pos, p.nrm, p.view, p.kd, p.ks = [a.ctypes.data for a in (mask, ro, pos, nrm, view, kd, ks)]
         p.light, p.pdf, p.rows, p.cols, p.perms = [a.ctypes.data for a in (light, pdf, rows, cols, perms)]
         p.scene = scene.h if scene is not None else None
+        if sampling_gbuffer is not None:       # test-only: (pos, nrm, kd, ks) used for the sampling decisions
+            sg_ = [self._a(x, full) for x in sampling_gbuffer]
+            keep += sg_
+            p.s_pos, p.s_nrm, p.s_kd, p.s_ks = [a.ctypes.data for a in sg_]
         cnt = np.zeros(3, np.uint64); p.counters = cnt.ctypes.data
         rec_t = rec_v = None
         if records:

@@ -1,0 +1,88 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference Python code from /root/reference in this
+container (CPU tensors):
+
+  * render/renderutils ops with use_python=True (render/renderutils/bsdf.py) -- forward values and every input
+    gradient through torch autograd, on the reference tests' input distribution (torch.rand, tests/test_bsdf.py);
+  * the PyTorch bilateral filter of render/optixutils/tests/filter_test.py:31-74: that script cannot be imported
+    (it runs at import time and needs CUDA), so its BilateralDenoiser class is extracted from the file's AST at
+    generation time, with device="cuda" replaced by "cpu" and its stale 11-channel input layout fed accordingly
+    (col, nrm, kd [ignored by the filter], zdz).  Nothing from the reference is copied into this repository.
+
+Run once (committed outputs travel to the GPU box, /root/reference does not):
+    python tests/golden/make_golden.py
+"""
+import ast
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+warnings.filterwarnings("ignore")
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(REF, "render"))
+import renderutils as ru  # noqa: E402  (the reference package; plugin compilation is lazy and never triggered here)
+
+RES = 8
+
+
+def rnd(gen, *shape):
+    return torch.rand(*shape, generator=gen, dtype=torch.float32)
+
+
+def run(fn, ins, name):
+    ins = [i.clone().requires_grad_(True) for i in ins]
+    out = fn(*ins)
+    g = torch.Generator().manual_seed(999)
+    dout = torch.rand(out.shape, generator=g)
+    out.backward(dout)
+    d = {"out": out.detach().numpy(), "dout": dout.numpy()}
+    for k, i in enumerate(ins):
+        d["in%d" % k] = i.detach().numpy()
+        d["grad%d" % k] = i.grad.numpy() if i.grad is not None else np.zeros_like(i.detach().numpy())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print("wrote", name, out.shape)
+
+
+def main():
+    gen = torch.Generator().manual_seed(0)
+    v3 = lambda: rnd(gen, 1, RES, RES, 3)
+    v1 = lambda: rnd(gen, 1, RES, RES, 1)
+    for bsdf in ("lambert", "frostbite"):
+        run(lambda *a: ru.pbr_bsdf(*a, bsdf=bsdf, use_python=True), [v3() for _ in range(6)], "ref_pbr_bsdf_" + bsdf)
+    run(lambda *a: ru.pbr_specular(*a, use_python=True), [v3(), v3(), v3(), v3(), v1()], "ref_pbr_specular")
+    run(lambda *a: ru.lambert(*a, use_python=True), [v3(), v3()], "ref_lambert")
+    run(lambda *a: ru.frostbite_diffuse(*a, use_python=True), [v3(), v3(), v3(), v1()], "ref_frostbite")
+    run(lambda *a: ru._fresnel_shlick(*a, use_python=True), [v3(), v3(), v1()], "ref_fresnel_shlick")
+    run(lambda *a: ru._ndf_ggx(*a, use_python=True), [v1(), v1()], "ref_ndf_ggx")
+    run(lambda *a: ru._lambda_ggx(*a, use_python=True), [v1(), v1()], "ref_lambda_ggx")
+    run(lambda *a: ru._masking_smith(*a, use_python=True), [v1(), v1(), v1()], "ref_masking_smith")
+    for ts, gl in ((True, True), (False, False)):
+        run(lambda *a: ru.prepare_shading_normal(*a, two_sided_shading=ts, opengl=gl, use_python=True), [v3() for _ in range(6)],
+            "ref_prepare_shading_normal_%d%d" % (ts, gl))
+
+    # ---- bilateral filter: class pulled out of the reference test script at run time ----
+    src = open(os.path.join(REF, "render/optixutils/tests/filter_test.py")).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, (ast.ClassDef, ast.FunctionDef)) and n.name in ("BilateralDenoiser", "dot")]
+    code = "\n".join(ast.get_source_segment(src, n) for n in keep).replace('device="cuda"', 'device="cpu"')
+    ns = {"torch": torch, "np": np, "math": __import__("math")}
+    exec(compile(code, "filter_test_extract", "exec"), ns)
+    H, W = 20, 27
+    col = rnd(gen, 1, H, W, 3) * 2
+    nrm = torch.nn.functional.normalize(rnd(gen, 1, H, W, 3) + torch.tensor([0.0, 0.0, 2.0]), dim=-1)
+    z = torch.cumsum(rnd(gen, 1, H, W, 1) * 0.05, dim=2)
+    dz = rnd(gen, 1, H, W, 1) * 0.05 + 0.01
+    kd = torch.ones(1, H, W, 3)
+    for sigma in (1.0, 2.0):
+        den = ns["BilateralDenoiser"](sigma=sigma)
+        out = den.forward(torch.cat([col, nrm, kd, z, dz], dim=-1))
+        np.savez_compressed(os.path.join(OUT, "ref_bilateral_sigma%d.npz" % int(sigma)), col=col.numpy(), nrm=nrm.numpy(),
+                            zdz=torch.cat([z, dz], -1).numpy(), sigma=np.float32(sigma), out=out.numpy())
+        print("wrote bilateral", sigma)
+
+
+if __name__ == "__main__":
+    main()
