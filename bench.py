@@ -260,11 +260,28 @@ def cpu_reference_step(o, case, N, sigma, seed):
     return float(d.sum())
 
 
+def host_cores():
+    """CPU threads this process may actually use (cgroup / affinity aware), also exported to OpenMP."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:                                   # cgroup v2 cpu quota
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    os.environ.setdefault("OMP_NUM_THREADS", str(n))
+    return n
+
+
 def run_reference(args, wl):
     """--impl reference: the reference's algorithm on the host CPUs (oracle port; OptiX cannot be built/run here)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = host_cores()
     from common import make_case, oracle
     o = oracle()
     N, res_s = wl["n_samples_x"], 128
@@ -279,7 +296,6 @@ def run_reference(args, wl):
         cpu_reference_step(o, case, N, wl["sigma"], 100 + i)
     dt = (time.time() - t0) / args.steps
     val = rays_step / dt / 1e6
-    cores = os.cpu_count()
     sample = "1 view at %dx%d of the same scene (same mesh, probe, n_samples_x=%d, sigma=%g): %d rays/step" % (res_s, res_s, N, wl["sigma"], rays_step)
     print(json.dumps({
         "impl": "reference", "metric": "shadow_rays_per_second_train_step", "value": round(val, 4), "unit": "Mrays/s", "n_gpus": args.gpus,
@@ -414,6 +430,7 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
+        ncores = host_cores()
         from common import make_case, oracle
         o = oracle()
         res_s = 96
@@ -425,7 +442,7 @@ def main():
         for i in range(reps):
             cpu_reference_step(o, case, N, wl["sigma"], 1 + i)
         dt = (time.time() - t0) / reps
-        cpu = {"value": round(cov * 2 * N * N * 2 / dt / 1e6, 4), "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "port",
+        cpu = {"value": round(cov * 2 * N * N * 2 / dt / 1e6, 4), "unit": "Mrays/s", "cores": ncores, "kind": "port",
                "sample": "same step on 1 view at %dx%d (%d rays/step), oracle C port with OpenMP" % (res_s, res_s, cov * 2 * N * N * 2)}
 
     out = {

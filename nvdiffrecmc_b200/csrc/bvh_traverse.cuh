@@ -15,6 +15,17 @@
 #pragma once
 #include "common.cuh"
 
+// 256-bit read-only global load (sm_100a: LDG.E.256): one L1 request + one 32-byte sector per lane instead of two.
+struct __align__(32) F8 { float4 a, b; };
+__device__ __forceinline__ F8 ldg256(const void *p)
+{
+    F8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+                 : "l"(p));
+    return r;
+}
+
 struct BvhView {
     const float4 *nodes;
     const float4 *tris;

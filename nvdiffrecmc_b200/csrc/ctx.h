@@ -27,6 +27,10 @@ struct mcs_ctx {
     // ---- traversal layout ----
     DevBuf nodes;                // [max(T-1,1)] x 4 float4 (two child boxes + child codes)
     DevBuf tris;                 // [T] x 3 float4 in SORTED order: (v0, orig id), (e1, -), (e2, -)
+    // ---- 8-wide compressed layout used by the shadow rays (bvh8.cuh) ----
+    DevBuf nodes8;               // [<= T] x 5 float4
+    DevBuf tris8;                // [T] x 3 float4 in wide-leaf order
+    DevBuf wide_bin;             // [<= T] binary node id of each wide node (build scratch)
     // ---- env_shade support ----
     DevBuf lcg_skip;             // [5*N*N+3] x uint2 (mul, add) LCG jump-ahead table for n_samples_x = skip_N
     int skip_N = 0;

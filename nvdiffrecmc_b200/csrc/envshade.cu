@@ -35,7 +35,7 @@
 //     reference's `+=`, kernel.cu:442-456) and scatters the env-map gradient with float atomics
 //     (kernel.cu:203-211), skipping zero contributions.
 #include "bsdf.cuh"
-#include "bvh_traverse.cuh"
+#include "bvh8.cuh"
 #include "ctx.h"
 #include "exact.cuh"
 #include <vector>
@@ -61,7 +61,7 @@ struct EnvParams {
     uint32_t bsdf, seed;
     int batch_offset;
     float shadow_scale;
-    BvhView bvh;
+    Bvh8View bvh;
     const uint2 *skip;
     unsigned int *chunk_counter;
     // fwd
@@ -255,15 +255,31 @@ __device__ __forceinline__ float warp_sum(float v)
 // ---------------------------------------------------------------------------------------------
 // Per-warp ray queue in shared memory (SoA, conflict-free: lane k touches word k of each array).
 // One "chunk" holds the live rays of up to MAX_PIX pixels (or a 256-item slice of one pixel when
-// 2*N^2 > 256).  tex bit 31 = "visible" flag written by the trace phase.
+// 2*N^2 > 256).  tex bit 31 = "occluded" flag written by the trace phase.
 // ---------------------------------------------------------------------------------------------
-constexpr int QCAP = 256;
+#ifndef MCS_LDG256
+#define MCS_LDG256 1
+#endif
+#ifndef MCS_QCAP
+#define MCS_QCAP 128
+#endif
+#ifndef MCS_LEAF_BATCH
+#define MCS_LEAF_BATCH 32
+#endif
+#ifndef MCS_REFILL_BELOW
+#define MCS_REFILL_BELOW 24
+#endif
+constexpr int QCAP = MCS_QCAP;
+constexpr int PCAP = 64;      // pending (ray, triangle-group) pairs: < 32 carried over + at most 32 appended per node step
+static_assert(QCAP <= 256, "queue entry index is packed into 8 bits");
 constexpr int MAX_PIX = 8;
 struct WarpQueue {
     float dx[QCAP], dy[QCAP], dz[QCAP], mis[QCAP];
     uint32_t tex[QCAP];
     uint16_t vlist[QCAP];       // dense list of entries that reach the eval phase
     uint16_t qpix[QCAP];        // pixel slot of the entry
+    uint32_t pl_tri[PCAP];      // deferred triangle tests: first triangle of the node's leaf block ...
+    uint32_t pl_mask[PCAP];     // ... and (triangle bit mask << 8) | queue entry
     float ro[MAX_PIX][3];
     float wo[MAX_PIX][3];
     int seg_end[MAX_PIX];
@@ -395,82 +411,99 @@ __device__ __forceinline__ void gen_segment(const EnvParams &p, WarpQueue &q, Wa
     }
 }
 
-// ---- phase T: any-hit traversal of all queued rays with dynamic ray fetch -------------------------
-// while-while traversal (Aila & Laine): lanes walk internal nodes until they reach a leaf or finish, then
-// test leaf triangles; a lane that finishes its ray pulls the next one from the warp queue as soon as fewer
-// than REFILL_BELOW lanes are busy, so the warp stays populated until the queue drains.
+// ---- phase T: any-hit traversal of all queued rays: dynamic ray fetch + deferred triangle tests --
+// SIMT-friendly organisation (profiles/r01_v2_*: a classic while-while loop ran at 13/32 lanes because lanes wait for each
+// other at every leaf; profiles/r01_v3_*: binary 64-byte nodes made every node fetch an L2 round trip):
+//   * node loop: every busy lane performs exactly one 8-wide node visit per iteration (bvh8.cuh: five 16-byte loads from an
+//     L1-resident node array, eight quantised slab tests).  Triangles of leaf children that pass are NOT intersected here:
+//     (ray, triangle block, bit mask) is appended to a per-warp pending list (ballot compaction) and the lane keeps walking,
+//     speculating that they miss;
+//   * as soon as 32 entries are pending the warp intersects them with all lanes busy; a hit sets the ray's "occluded" bit
+//     (tex bit 31), which the owning lane polls once per node visit to abandon the walk;
+//   * a lane whose walk ends pulls the next queued ray when fewer than REFILL_BELOW lanes are busy;
+//   * visibility of a ray = its occluded bit after the queue AND the pending list have drained.
 __device__ __forceinline__ void trace_queue(const EnvParams &p, WarpQueue &q, const int qn, const int lane)
 {
-    constexpr int REFILL_BELOW = 24;
-    constexpr int DONE = 0x7FFFFFFF;
-    int head = 0;
+    constexpr int REFILL_BELOW = MCS_REFILL_BELOW;
+    constexpr int LEAF_BATCH = MCS_LEAF_BATCH;
+    const unsigned lt = (1u << lane) - 1u;
+    int head = 0, pend = 0;
     int my = -1;
-    int node = DONE, sp = 0;
-    int stack[MCS_STACK];
-    f3 o = F3(0.0f), d = F3(0.0f);
-    RayPre r = ray_pre(F3(0.0f), F3(1.0f));
-    const BvhView b = p.bvh;
+    Trav8 t;
+    t.start();
+    uint2 stack[MCS_STACK8];
+    Ray8 r = ray8_pre(F3(0.0f), F3(1.0f));
+    const Bvh8View b = p.bvh;
+
+    auto tri_batch = [&](int n) {
+        // intersect the last n (<= 32) pending triangle groups, one per lane
+        __syncwarp();
+        const int base = pend - n;
+        if (lane < n) {
+            const uint32_t pm = q.pl_mask[base + lane];
+            const int e = (int)(pm & 0xFFu);
+            if (!(q.tex[e] >> 31)) {
+                const uint32_t tb = q.pl_tri[base + lane];
+                uint32_t tm = pm >> 8;
+                const int ps = q.qpix[e];
+                const f3 o = F3(q.ro[ps][0], q.ro[ps][1], q.ro[ps][2]);
+                const f3 d = F3(q.dx[e], q.dy[e], q.dz[e]);
+                bool hit = false;
+                while (tm && !hit) {
+                    const int k = __ffs((int)tm) - 1;
+                    tm &= tm - 1;
+                    const float4 *tp = b.tris + 3 * (size_t)(tb + k);
+                    const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                    float tt, uu, vv;
+                    hit = mt_hit(o, d, F3(t0.x, t0.y, t0.z), F3(t1.x, t1.y, t1.z), F3(t2.x, t2.y, t2.z), MCS_TMAX, tt, uu, vv);
+                }
+                if (hit) atomicOr(&q.tex[e], 0x80000000u);
+            }
+        }
+        pend = base;
+        __syncwarp();
+    };
+
     while (true) {
         // refill idle lanes
         const unsigned idle = __ballot_sync(0xFFFFFFFFu, my < 0);
         if (idle && head < qn) {
-            const int idx = head + __popc(idle & ((1u << lane) - 1u));
+            const int idx = head + __popc(idle & lt);
             if (my < 0 && idx < qn) {
                 my = idx;
                 const int ps = q.qpix[idx];
-                o = F3(q.ro[ps][0], q.ro[ps][1], q.ro[ps][2]);
-                d = F3(q.dx[idx], q.dy[idx], q.dz[idx]);
-                r = ray_pre(o, d);
-                node = 0; sp = 0;
+                r = ray8_pre(F3(q.ro[ps][0], q.ro[ps][1], q.ro[ps][2]), F3(q.dx[idx], q.dy[idx], q.dz[idx]));
+                t.start();
             }
             head += __popc(idle);
         }
-        if (__ballot_sync(0xFFFFFFFFu, my >= 0) == 0u) break;
+        int nact = __popc(__ballot_sync(0xFFFFFFFFu, my >= 0));
+        if (nact == 0) {
+            if (pend == 0) break;
+            tri_batch(pend < 32 ? pend : 32);         // final flush (queue exhausted, no walker left)
+            continue;
+        }
         const int thresh = head < qn ? REFILL_BELOW : 1;
         do {
-            // internal nodes
-            while (node >= 0 && node != DONE) {
-                const float4 *n = b.nodes + 4 * (size_t)node;
-                const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
-                float a0 = fmaf(q0.x, r.ix, -r.ox), a1 = fmaf(q0.y, r.ix, -r.ox);
-                float b0 = fmaf(q0.z, r.iy, -r.oy), b1 = fmaf(q0.w, r.iy, -r.oy);
-                float c0 = fmaf(q2.x, r.iz, -r.oz), c1 = fmaf(q2.y, r.iz, -r.oz);
-                const float tn0 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
-                const float tf0 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), MCS_TMAX));
-                a0 = fmaf(q1.x, r.ix, -r.ox); a1 = fmaf(q1.y, r.ix, -r.ox);
-                b0 = fmaf(q1.z, r.iy, -r.oy); b1 = fmaf(q1.w, r.iy, -r.oy);
-                c0 = fmaf(q2.z, r.iz, -r.oz); c1 = fmaf(q2.w, r.iz, -r.oz);
-                const float tn1 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
-                const float tf1 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), MCS_TMAX));
-                const bool h0 = tn0 <= tf0 * 1.0000004f, h1 = tn1 <= tf1 * 1.0000004f;
-                const int ch0 = __float_as_int(q3.x), ch1 = __float_as_int(q3.y);
-                if (h0 && h1) {
-                    const bool first0 = tn0 <= tn1;
-                    stack[sp++] = first0 ? ch1 : ch0;
-                    node = first0 ? ch0 : ch1;
-                } else if (h0) node = ch0;
-                else if (h1) node = ch1;
-                else node = sp ? stack[--sp] : DONE;
+            uint32_t tmask = 0, tbase = 0;
+            const int cur = my;
+            if (my >= 0 && (q.tex[my] >> 31)) my = -1;      // a deferred triangle test already found an occluder
+            if (my >= 0) {
+                int idx;
+                if (trav8_next(t, stack, idx)) {
+                    uint32_t cb, im;
+                    const uint32_t hits = bvh8_visit(b.nodes, idx, r, cb, tbase, im);
+                    t.ng = make_uint2(cb, (hits & 0xFF000000u) | im);
+                    tmask = hits & 0x00FFFFFFu;
+                } else my = -1;                              // walk finished; verdict comes from the occluded bit
             }
-            // leaf: a run of consecutive triangles in Morton order
-            if (node < 0) {
-                const int code = ~node;
-                const int start = code >> 3, cnt = (code & 7) + 1;
-                bool hit = false;
-                for (int k = 0; k < cnt && !hit; ++k) {
-                    const float4 *t = b.tris + 3 * (size_t)(start + k);
-                    const float4 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2);
-                    float tt, uu, vv;
-                    hit = mt_hit(o, d, F3(t0.x, t0.y, t0.z), F3(t1.x, t1.y, t1.z), F3(t2.x, t2.y, t2.z), MCS_TMAX, tt, uu, vv);
-                }
-                if (hit) { node = DONE; sp = -1; }            // occluded
-                else node = sp ? stack[--sp] : DONE;
-            }
-            if (node == DONE && my >= 0) {
-                if (sp == 0) q.tex[my] |= 0x80000000u;        // stack ran empty without a hit: visible
-                my = -1;
-            }
-        } while ((int)__popc(__ballot_sync(0xFFFFFFFFu, my >= 0)) >= thresh);
+            // defer the triangle tests
+            const unsigned mA = __ballot_sync(0xFFFFFFFFu, tmask != 0u);
+            if (tmask) { const int e = pend + __popc(mA & lt); q.pl_tri[e] = tbase; q.pl_mask[e] = (tmask << 8) | (uint32_t)cur; }
+            pend += __popc(mA);
+            nact = __popc(__ballot_sync(0xFFFFFFFFu, my >= 0));
+        } while (pend < LEAF_BATCH && nact >= thresh);
+        while (pend >= LEAF_BATCH) tri_batch(pend < 32 ? pend : 32);
     }
     __syncwarp();
 }
@@ -555,15 +588,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MCS_ENV_OCC) env_shade_ker
                 }
                 __syncwarp();
                 // ================= phase T =================
-                if (trace_needed) trace_queue(p, q, qn, lane);
-                else {
-                    for (int e = lane; e < qn; e += 32) q.tex[e] |= 0x80000000u;
-                    __syncwarp();
-                }
+                if (trace_needed) trace_queue(p, q, qn, lane);        // sets tex bit 31 of occluded rays
                 if (MODE == 2) {
                     for (int e = lane; e < qn; e += 32) {
                         const size_t rec = (size_t)q.pixid[q.qpix[e]] * items + qr->slot[e];
-                        p.rec_vis[rec] = trace_needed ? (uint8_t)(q.tex[e] >> 31) : (uint8_t)2;
+                        p.rec_vis[rec] = trace_needed ? (uint8_t)(1u - (q.tex[e] >> 31)) : (uint8_t)2;
                     }
                 }
                 // ================= phase E =================
@@ -574,7 +603,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MCS_ENV_OCC) env_shade_ker
                     int vn = 0;
                     for (int e0 = s0; e0 < s1; e0 += 32) {
                         const int e = e0 + lane;
-                        const bool keep = e < s1 && ((q.tex[e] >> 31) || v_occluded != 0.0f);
+                        const bool keep = e < s1 && (!(q.tex[e] >> 31) || v_occluded != 0.0f);
                         const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
                         if (keep) q.vlist[s0 + vn + __popc(m & ((1u << lane) - 1u))] = (uint16_t)e;
                         vn += __popc(m);
@@ -591,7 +620,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MCS_ENV_OCC) env_shade_ker
                         const f3 wi = F3(q.dx[e], q.dy[e], q.dz[e]);
                         const uint32_t tex = q.tex[e];
                         const int tx = tex & 0xFFFFu, ty = (tex >> 16) & 0x7FFFu;
-                        const float Vv = (tex >> 31) ? 1.0f : v_occluded;
+                        const float Vv = (tex >> 31) ? v_occluded : 1.0f;
                         const float wgt = Vv * q.mis[e] * sample_frac;
                         // process_sample, kernel.cu:403-461
                         const float *lp = p.light + (size_t)ty * p.l_s1 + (size_t)tx * p.l_s2;
@@ -717,7 +746,7 @@ static int fill_params(mcs_ctx *ctx, EnvParams &p,
     p.perms = (const int32_t *)perms->ptr; p.pm_s1 = perms->strides[1]; p.pm_s3 = perms->strides[3]; p.n_perms = (uint32_t)perms->sizes[1];
     p.m_rows = cdf_iters(p.Hl); p.m_cols = cdf_iters(p.Wl);
     p.bsdf = bsdf; p.seed = rnd_seed; p.batch_offset = batch_offset; p.shadow_scale = shadow_scale;
-    p.bvh = BvhView{(const float4 *)ctx->nodes.p, (const float4 *)ctx->tris.p};
+    p.bvh = Bvh8View{(const float4 *)ctx->nodes8.p, (const float4 *)ctx->tris8.p};
     if (int e = ensure_skip_table(ctx, p.N, s)) return e;
     p.skip = (const uint2 *)((const char *)ctx->lcg_skip.p);
     if (int e = mcs_buf_reserve(ctx->light_grad4, 256, s)) return e;

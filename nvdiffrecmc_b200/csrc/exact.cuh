@@ -69,7 +69,10 @@ __device__ __forceinline__ double xd_add(double a, double b) { return __dadd_rn(
 __device__ __forceinline__ double xd_div(double a, double b) { return __ddiv_rn(a, b); }
 
 // ---- deterministic transcendentals (spec: DESIGN.md; oracle twin: oracle/detmath.h) -------------
-__device__ __forceinline__ void det_sincos(xf a, xf &s, xf &c)
+#ifndef MCS_DET_INLINE
+#define MCS_DET_INLINE __forceinline__
+#endif
+__device__ MCS_DET_INLINE void det_sincos(xf a, xf &s, xf &c)
 {
     xf k = xf(rintf((a * xf(0.636619772367581343f)).v));
     int q = (int)k.v;
@@ -96,7 +99,7 @@ __device__ __forceinline__ xf det_atan_pos(xf t)
     xf y = (((xf(8.05374449538e-2f) * z - xf(1.38776856032e-1f)) * z + xf(1.99777106478e-1f)) * z - xf(3.33329491539e-1f)) * z * t + t;
     return y0 + y;
 }
-__device__ __forceinline__ xf det_atan2(xf y, xf x)
+__device__ MCS_DET_INLINE xf det_atan2(xf y, xf x)
 {
     if (x.v == 0.0f && y.v == 0.0f) return xf(0.0f);
     xf a = det_atan_pos(xf(fabsf(y.v)) / xf(fabsf(x.v)));
@@ -108,7 +111,7 @@ __device__ __forceinline__ xf det_asin_kernel(xf a)
     xf z = a * a;
     return ((((xf(4.2163199048e-2f) * z + xf(2.4181311049e-2f)) * z + xf(4.5470025998e-2f)) * z + xf(7.4953002686e-2f)) * z + xf(1.6666752422e-1f)) * z * a + a;
 }
-__device__ __forceinline__ xf det_acos(xf x)
+__device__ MCS_DET_INLINE xf det_acos(xf x)
 {
     if (x.v < -0.5f) return xf(3.14159265358979323846f) - xf(2.0f) * det_asin_kernel(xsqrt(xf(0.5f) * (xf(1.0f) + x)));
     if (x.v > 0.5f) return xf(2.0f) * det_asin_kernel(xsqrt(xf(0.5f) * (xf(1.0f) - x)));
