@@ -5,21 +5,17 @@
 // env_shade_bwd (render/optixutils/c_src/torch_bindings.cpp:123-272).
 //
 // B200 mapping (no RT cores, 148 SMs):
-//   * ONE WARP PER PIXEL GROUP, ONE LANE PER SAMPLE, THREE PHASES PER GROUP (v2, see profiles/r01_v1_*: the v1 kernel
-//     traced inline and ran its traversal loop at 10/32 active lanes):
-//       G  generate: all lanes draw samples (exact path), rays that can contribute (n.wi > 0) are compacted into a
-//          per-warp shared-memory queue (direction, env texel, MIS weight) -- up to 256 rays = 2 pixels at N=8;
-//       T  trace: while-while BVH traversal with dynamic fetch -- a lane that finishes pulls the next queued ray,
-//          so traversal runs with (nearly) full warps until the queue drains; the result is one bit per ray;
-//       E  evaluate: surviving rays (V != 0) are compacted again and only those evaluate the BSDF (forward) or its
-//          adjoint + the env-map gradient scatter (backward), then warp-shuffle reduction, one writer per pixel.
-//     The reference runs one thread per pixel and loops
-//     2*N^2 samples serially; here the 2*N^2 (stratum, sample-type) items of a pixel are spread over
-//     the 32 lanes (items [0,N^2) are light samples, [N^2,2N^2) BSDF samples, so a 32-item round is
-//     type-uniform whenever N^2 is a multiple of 32).  All rays of a warp share their origin, which
-//     keeps the top of the BVH walk coherent, and the per-pixel G-buffer record is loaded once per
-//     warp with broadcast loads.  Per-lane partial sums are combined with warp shuffles and written
-//     once: no G-buffer round trip, no atomics except the env-map gradient.
+//   * ONE CTA PER SM (32 warps), ONE WARP PER PIXEL, ONE LANE PER SAMPLE, THREE BLOCK-SYNCHRONOUS PHASES PER BATCH OF 32 PIXELS
+//     (history in profiles/: v1 traced inline at 10/32 active lanes; v2 per-warp queues, 13/32 lanes in the while-while loop;
+//      v3 deferred leaf tests, 25/32 lanes but 22 % instruction-fetch stalls with warps spread over all phases):
+//       G  generate: every warp draws the 2N^2 samples of its pixel (exact path, all lanes); rays that can contribute
+//          (n.wi > 0) are ballot-compacted into the warp's segment of a block-wide shared-memory queue (direction, env
+//          texel, MIS weight);
+//       T  trace: all warps drain the queue together -- own segment first, then work stealing -- with one binary-BVH node
+//          step per lane per iteration, leaf tests deferred to full-warp batches, dynamic ray fetch;  one bit per ray;
+//       E  evaluate: each warp compacts the surviving rays (V != 0) of its pixel and only those evaluate the BSDF (forward)
+//          or its adjoint + the env-map gradient scatter (backward); warp-shuffle reduction, one writer per pixel.
+//     The reference runs one thread per pixel and loops 2*N^2 samples serially with an optixTrace per sample.
 //   * The reference's per-pixel PCG stream is sequential (5 uniforms per stratum); lanes jump to their
 //     position with a precomputed LCG skip table (state' = state*mul[k] + add[k]), so the random
 //     numbers are bit-identical to the reference stream (kernel.cu:30-45, 504-524).
@@ -35,17 +31,13 @@
 //     reference's `+=`, kernel.cu:442-456) and scatters the env-map gradient with float atomics
 //     (kernel.cu:203-211), skipping zero contributions.
 #include "bsdf.cuh"
-#include "bvh8.cuh"
+#include "bvh_traverse.cuh"
 #include "ctx.h"
 #include "exact.cuh"
 #include <vector>
 
 namespace {
 
-#ifndef MCS_ENV_OCC
-#define MCS_ENV_OCC 4
-#endif
-constexpr int WARPS_PER_CTA = 8;
 constexpr float MIN_ROUGHNESS = 0.08f;     // kernel.cu:17
 
 struct EnvParams {
@@ -61,7 +53,7 @@ struct EnvParams {
     uint32_t bsdf, seed;
     int batch_offset;
     float shadow_scale;
-    Bvh8View bvh;
+    BvhView bvh;
     const uint2 *skip;
     unsigned int *chunk_counter;
     // fwd
@@ -253,15 +245,16 @@ __device__ __forceinline__ float warp_sum(float v)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Per-warp ray queue in shared memory (SoA, conflict-free: lane k touches word k of each array).
-// One "chunk" holds the live rays of up to MAX_PIX pixels (or a 256-item slice of one pixel when
-// 2*N^2 > 256).  tex bit 31 = "occluded" flag written by the trace phase.
+// Block-wide ray queue in shared memory.  One CTA = NW warps = one SM's worth of threads (1 CTA/SM, 64 registers).
+// All warps of the CTA move through the three phases TOGETHER (barriers in between):
+//   * the instruction working set at any time is one phase, shared by all resident warps (profiles/r01_v3_*: with warps
+//     spread over G/T/E code, 22 % of all stall samples were instruction-fetch misses);
+//   * the trace phase load-balances over the whole SM: warp w owns segment w of the queue (the live rays of "its" pixel),
+//     drains it first and then steals from the other segments, so no lane idles while any ray of the batch is untraced.
+// Layout is SoA, conflict-free: lane k of a warp touches word k of a segment.  tex bit 31 = "occluded" flag (trace phase).
 // ---------------------------------------------------------------------------------------------
-#ifndef MCS_LDG256
-#define MCS_LDG256 1
-#endif
-#ifndef MCS_QCAP
-#define MCS_QCAP 128
+#ifndef MCS_CTA_WARPS
+#define MCS_CTA_WARPS 32
 #endif
 #ifndef MCS_LEAF_BATCH
 #define MCS_LEAF_BATCH 32
@@ -269,23 +262,28 @@ __device__ __forceinline__ float warp_sum(float v)
 #ifndef MCS_REFILL_BELOW
 #define MCS_REFILL_BELOW 24
 #endif
-constexpr int QCAP = MCS_QCAP;
-constexpr int PCAP = 64;      // pending (ray, triangle-group) pairs: < 32 carried over + at most 32 appended per node step
-static_assert(QCAP <= 256, "queue entry index is packed into 8 bits");
-constexpr int MAX_PIX = 8;
-struct WarpQueue {
-    float dx[QCAP], dy[QCAP], dz[QCAP], mis[QCAP];
-    uint32_t tex[QCAP];
-    uint16_t vlist[QCAP];       // dense list of entries that reach the eval phase
-    uint16_t qpix[QCAP];        // pixel slot of the entry
-    uint32_t pl_tri[PCAP];      // deferred triangle tests: first triangle of the node's leaf block ...
-    uint32_t pl_mask[PCAP];     // ... and (triangle bit mask << 8) | queue entry
-    float ro[MAX_PIX][3];
-    float wo[MAX_PIX][3];
-    int seg_end[MAX_PIX];
-    int pixid[MAX_PIX];         // linear pixel index of each slot
+constexpr int NW = MCS_CTA_WARPS;
+constexpr int SEG = 128;                 // queue entries per warp segment (= one pixel at N = 8)
+constexpr int QTOT = NW * SEG;
+constexpr int PCAP = 128;                // pending (ray, leaf) pairs per warp: < 32 carried over + at most 64 appended per node step
+constexpr int PIXRING = 256;
+static_assert(QTOT <= 65536, "queue entry index is stored in 16 bits");
+
+struct BlockQueue {
+    float dx[QTOT], dy[QTOT], dz[QTOT], mis[QTOT];
+    uint32_t tex[QTOT];
+    uint16_t vlist[QTOT];                // per segment: dense list of entries that reach the eval phase
+    uint16_t pl_ray[NW][PCAP];           // per warp: deferred leaf tests, queue entry ...
+    int pl_leaf[NW][PCAP];               // ... and leaf code
+    float ro[NW][3];                     // per segment: ray origin / view vector / pixel id / live-ray count / fetch cursor
+    float wo[NW][3];
+    int pixid[NW];
+    int seg_cnt[NW];
+    int seg_head[NW];
+    int pixring[PIXRING];                // active pixels waiting for a batch
+    int ring_head, ring_tail, more_chunks;
 };
-struct WarpQueueRec { uint32_t slot[QCAP]; };   // MODE 2 only
+struct BlockQueueRec { uint32_t slot[QTOT]; };   // MODE 2 only
 
 struct PixelIn {
     f3 ro, pos, nrm, view, kd, ks;
@@ -342,12 +340,13 @@ __device__ __forceinline__ void make_frame(const PixelIn &q, PixelFrame &f)
     f.NdotV = xdot(f.N, f.wo);
 }
 
-// ---- phase G: generate the items [w0, w1) of one pixel, push the rays that can contribute ----------
+// ---- phase G: generate the items [w0, w1) of one pixel, push the rays that can contribute into segment `seg` ----------
 template <int MODE>
-__device__ __forceinline__ void gen_segment(const EnvParams &p, WarpQueue &q, WarpQueueRec *qr, const PixelIn &px, const PixelFrame &f,
-                                            int slot, int w0, int w1, int &qn, const int lane)
+__device__ __forceinline__ void gen_segment(const EnvParams &p, BlockQueue &q, BlockQueueRec *qr, const PixelIn &px, const PixelFrame &f,
+                                            int seg, int w0, int w1, int &qn, const int lane)
 {
     const int S = p.S;
+    const int qb = seg * SEG;
     const xf strata_frac = xf(1.0f) / xf((float)(unsigned)p.N);
     // RNG, kernel.cu:504-505
     uint32_t s_seed = p.seed, s_pix = (uint32_t)(((px.iz + p.batch_offset) * p.H + px.iy) * p.W + px.ix);
@@ -400,60 +399,62 @@ __device__ __forceinline__ void gen_segment(const EnvParams &p, WarpQueue &q, Wa
         }
         const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
         if (live) {
-            const int e = qn + __popc(m & ((1u << lane) - 1u));
+            const int e = qb + qn + __popc(m & ((1u << lane) - 1u));
             q.dx[e] = wi.x; q.dy[e] = wi.y; q.dz[e] = wi.z;
             q.mis[e] = 1.0f / fmaxf(pdf_sum, 0.0001f);          // MIS balance heuristic, kernel.cu:409
             q.tex[e] = (uint32_t)((ty << 16) | tx);
-            q.qpix[e] = (uint16_t)slot;
             if (MODE == 2) qr->slot[e] = (uint32_t)(2 * i + (is_bsdf ? 1 : 0));
         }
         qn += __popc(m);
     }
 }
 
-// ---- phase T: any-hit traversal of all queued rays: dynamic ray fetch + deferred triangle tests --
+// ---- phase T: any-hit traversal of all queued rays of the CTA: work stealing + dynamic fetch + deferred leaf tests ----
 // SIMT-friendly organisation (profiles/r01_v2_*: a classic while-while loop ran at 13/32 lanes because lanes wait for each
-// other at every leaf; profiles/r01_v3_*: binary 64-byte nodes made every node fetch an L2 round trip):
-//   * node loop: every busy lane performs exactly one 8-wide node visit per iteration (bvh8.cuh: five 16-byte loads from an
-//     L1-resident node array, eight quantised slab tests).  Triangles of leaf children that pass are NOT intersected here:
-//     (ray, triangle block, bit mask) is appended to a per-warp pending list (ballot compaction) and the lane keeps walking,
-//     speculating that they miss;
-//   * as soon as 32 entries are pending the warp intersects them with all lanes busy; a hit sets the ray's "occluded" bit
-//     (tex bit 31), which the owning lane polls once per node visit to abandon the walk;
-//   * a lane whose walk ends pulls the next queued ray when fewer than REFILL_BELOW lanes are busy;
-//   * visibility of a ray = its occluded bit after the queue AND the pending list have drained.
-__device__ __forceinline__ void trace_queue(const EnvParams &p, WarpQueue &q, const int qn, const int lane)
+// other at every leaf):
+//   * node loop: every busy lane performs exactly one node step per iteration (fetch a 64-byte node holding both children's
+//     boxes, two slab tests, descend / push / pop).  Leaf children that pass the slab test are NOT intersected here: the
+//     (ray, leaf) pair is appended to the warp's pending list (ballot compaction) and the lane keeps walking, speculating
+//     that the leaf misses;
+//   * as soon as 32 pairs are pending the warp intersects them with all lanes busy; a hit sets the ray's "occluded" bit
+//     (tex bit 31), which the owning lane polls once per node step to abandon the walk;
+//   * a lane whose walk ends pulls the next ray -- from the warp's own segment first, then from the other warps' segments --
+//     as soon as fewer than REFILL_BELOW lanes are busy;
+//   * visibility of a ray = its occluded bit after all segments AND all pending lists have drained (block barrier).
+// (An 8-wide compressed BVH, bvh8.cuh, was measured too: it removes the L2 round trips but its unrolled node test is
+//  instruction-fetch bound and ended up 15 % slower; profiles/r01_bvh8_*.)
+__device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, const int warp, const int lane)
 {
     constexpr int REFILL_BELOW = MCS_REFILL_BELOW;
     constexpr int LEAF_BATCH = MCS_LEAF_BATCH;
+    constexpr int DONE = 0x7FFFFFFF;
     const unsigned lt = (1u << lane) - 1u;
-    int head = 0, pend = 0;
+    int pend = 0;
     int my = -1;
-    Trav8 t;
-    t.start();
-    uint2 stack[MCS_STACK8];
-    Ray8 r = ray8_pre(F3(0.0f), F3(1.0f));
-    const Bvh8View b = p.bvh;
+    int node = DONE, sp = 0;
+    int stack[MCS_STACK];
+    RayPre r = ray_pre(F3(0.0f), F3(1.0f));
+    const BvhView b = p.bvh;
+    uint16_t *pl_ray = q.pl_ray[warp];
+    int *pl_leaf = q.pl_leaf[warp];
+    int seg = warp, exhausted = 0;           // segment being drained, number of segments found empty so far
 
-    auto tri_batch = [&](int n) {
-        // intersect the last n (<= 32) pending triangle groups, one per lane
+    auto leaf_batch = [&](int n) {
+        // intersect the last n (<= 32) pending pairs, one per lane
         __syncwarp();
         const int base = pend - n;
         if (lane < n) {
-            const uint32_t pm = q.pl_mask[base + lane];
-            const int e = (int)(pm & 0xFFu);
+            const int e = pl_ray[base + lane];
             if (!(q.tex[e] >> 31)) {
-                const uint32_t tb = q.pl_tri[base + lane];
-                uint32_t tm = pm >> 8;
-                const int ps = q.qpix[e];
+                const int code = ~pl_leaf[base + lane];
+                const int start = code >> 3, cnt = (code & 7) + 1;
+                const int ps = e / SEG;
                 const f3 o = F3(q.ro[ps][0], q.ro[ps][1], q.ro[ps][2]);
                 const f3 d = F3(q.dx[e], q.dy[e], q.dz[e]);
                 bool hit = false;
-                while (tm && !hit) {
-                    const int k = __ffs((int)tm) - 1;
-                    tm &= tm - 1;
-                    const float4 *tp = b.tris + 3 * (size_t)(tb + k);
-                    const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                for (int k = 0; k < cnt && !hit; ++k) {
+                    const float4 *t = b.tris + 3 * (size_t)(start + k);
+                    const float4 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2);
                     float tt, uu, vv;
                     hit = mt_hit(o, d, F3(t0.x, t0.y, t0.z), F3(t1.x, t1.y, t1.z), F3(t2.x, t2.y, t2.z), MCS_TMAX, tt, uu, vv);
                 }
@@ -465,57 +466,87 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, WarpQueue &q, co
     };
 
     while (true) {
-        // refill idle lanes
-        const unsigned idle = __ballot_sync(0xFFFFFFFFu, my < 0);
-        if (idle && head < qn) {
-            const int idx = head + __popc(idle & lt);
-            if (my < 0 && idx < qn) {
+        // ---- refill idle lanes: own segment first, then steal ----
+        unsigned idle = __ballot_sync(0xFFFFFFFFu, my < 0);
+        while (idle && exhausted < NW) {
+            const int need = __popc(idle);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&q.seg_head[seg], need);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            const int avail = q.seg_cnt[seg] - base;
+            if (avail <= 0) { seg = seg + 1 == NW ? 0 : seg + 1; ++exhausted; continue; }
+            const int take = avail < need ? avail : need;
+            const int rank = __popc(idle & lt);
+            if (my < 0 && rank < take) {
+                const int idx = seg * SEG + base + rank;
                 my = idx;
-                const int ps = q.qpix[idx];
-                r = ray8_pre(F3(q.ro[ps][0], q.ro[ps][1], q.ro[ps][2]), F3(q.dx[idx], q.dy[idx], q.dz[idx]));
-                t.start();
+                r = ray_pre(F3(q.ro[seg][0], q.ro[seg][1], q.ro[seg][2]), F3(q.dx[idx], q.dy[idx], q.dz[idx]));
+                node = 0; sp = 0;
             }
-            head += __popc(idle);
+            if (take < need) { seg = seg + 1 == NW ? 0 : seg + 1; ++exhausted; }
+            idle = __ballot_sync(0xFFFFFFFFu, my < 0);
         }
         int nact = __popc(__ballot_sync(0xFFFFFFFFu, my >= 0));
         if (nact == 0) {
             if (pend == 0) break;
-            tri_batch(pend < 32 ? pend : 32);         // final flush (queue exhausted, no walker left)
+            leaf_batch(pend < 32 ? pend : 32);        // final flush (nothing left to fetch, no walker left)
             continue;
         }
-        const int thresh = head < qn ? REFILL_BELOW : 1;
+        const int thresh = exhausted < NW ? REFILL_BELOW : 1;
         do {
-            uint32_t tmask = 0, tbase = 0;
+            bool hasA = false, hasB = false;
+            int leafA = 0, leafB = 0;
             const int cur = my;
-            if (my >= 0 && (q.tex[my] >> 31)) my = -1;      // a deferred triangle test already found an occluder
+            if (my >= 0 && (q.tex[my] >> 31)) my = -1;      // a deferred leaf test already found an occluder
             if (my >= 0) {
-                int idx;
-                if (trav8_next(t, stack, idx)) {
-                    uint32_t cb, im;
-                    const uint32_t hits = bvh8_visit(b.nodes, idx, r, cb, tbase, im);
-                    t.ng = make_uint2(cb, (hits & 0xFF000000u) | im);
-                    tmask = hits & 0x00FFFFFFu;
-                } else my = -1;                              // walk finished; verdict comes from the occluded bit
+                const float4 *n = b.nodes + 4 * (size_t)node;
+                const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
+                float a0 = fmaf(q0.x, r.ix, -r.ox), a1 = fmaf(q0.y, r.ix, -r.ox);
+                float b0 = fmaf(q0.z, r.iy, -r.oy), b1 = fmaf(q0.w, r.iy, -r.oy);
+                float c0 = fmaf(q2.x, r.iz, -r.oz), c1 = fmaf(q2.y, r.iz, -r.oz);
+                const float tn0 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
+                const float tf0 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), MCS_TMAX));
+                a0 = fmaf(q1.x, r.ix, -r.ox); a1 = fmaf(q1.y, r.ix, -r.ox);
+                b0 = fmaf(q1.z, r.iy, -r.oy); b1 = fmaf(q1.w, r.iy, -r.oy);
+                c0 = fmaf(q2.z, r.iz, -r.oz); c1 = fmaf(q2.w, r.iz, -r.oz);
+                const float tn1 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
+                const float tf1 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), MCS_TMAX));
+                const bool h0 = tn0 <= tf0 * 1.0000004f, h1 = tn1 <= tf1 * 1.0000004f;
+                const int ch0 = __float_as_int(q3.x), ch1 = __float_as_int(q3.y);
+                hasA = h0 && ch0 < 0; leafA = ch0;
+                hasB = h1 && ch1 < 0; leafB = ch1;
+                const bool i0 = h0 && ch0 >= 0, i1 = h1 && ch1 >= 0;
+                if (i0 && i1) {
+                    const bool first0 = tn0 <= tn1;        // nearer child first
+                    stack[sp++] = first0 ? ch1 : ch0;
+                    node = first0 ? ch0 : ch1;
+                } else if (i0) node = ch0;
+                else if (i1) node = ch1;
+                else if (sp) node = stack[--sp];
+                else my = -1;                               // walk finished; verdict comes from the occluded bit
             }
-            // defer the triangle tests
-            const unsigned mA = __ballot_sync(0xFFFFFFFFu, tmask != 0u);
-            if (tmask) { const int e = pend + __popc(mA & lt); q.pl_tri[e] = tbase; q.pl_mask[e] = (tmask << 8) | (uint32_t)cur; }
+            // defer the leaf tests
+            const unsigned mA = __ballot_sync(0xFFFFFFFFu, hasA);
+            if (hasA) { const int e = pend + __popc(mA & lt); pl_ray[e] = (uint16_t)cur; pl_leaf[e] = leafA; }
             pend += __popc(mA);
+            const unsigned mB = __ballot_sync(0xFFFFFFFFu, hasB);
+            if (hasB) { const int e = pend + __popc(mB & lt); pl_ray[e] = (uint16_t)cur; pl_leaf[e] = leafB; }
+            pend += __popc(mB);
             nact = __popc(__ballot_sync(0xFFFFFFFFu, my >= 0));
         } while (pend < LEAF_BATCH && nact >= thresh);
-        while (pend >= LEAF_BATCH) tri_batch(pend < 32 ? pend : 32);
+        while (pend >= LEAF_BATCH) leaf_batch(32);
     }
     __syncwarp();
 }
 
 // MODE 0: forward, 1: backward, 2: forward + per-ray records
 template <int MODE>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MCS_ENV_OCC) env_shade_kernel(const EnvParams p)
+__global__ void __launch_bounds__(NW * 32, 1) env_shade_kernel(const EnvParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpQueue &q = reinterpret_cast<WarpQueue *>(smem_raw)[warp];
-    WarpQueueRec *qr = MODE == 2 ? reinterpret_cast<WarpQueueRec *>(smem_raw + sizeof(WarpQueue) * WARPS_PER_CTA) + warp : nullptr;
+    BlockQueue &q = *reinterpret_cast<BlockQueue *>(smem_raw);
+    BlockQueueRec *qr = MODE == 2 ? reinterpret_cast<BlockQueueRec *>(smem_raw + sizeof(BlockQueue)) : nullptr;
 
     const int64_t npix = (int64_t)p.B * p.H * p.W;
     const unsigned int nchunks = (unsigned int)((npix + 31) / 32);
@@ -524,159 +555,167 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MCS_ENV_OCC) env_shade_ker
     const bool diffuse_only = (p.bsdf == 1u || p.bsdf == 2u);
     const bool trace_needed = p.shadow_scale != 0.0f;
     const float v_occluded = 1.0f - p.shadow_scale;          // V of an occluded ray (kernel.cu:420)
-    // pixels whose rays are traced together
-    const int group = items <= QCAP ? min(MAX_PIX, QCAP / items) : 1;
+    const int nsub = (items + SEG - 1) / SEG;                // queue fills per pixel (1 for N <= 8)
+    const int qb = warp * SEG;
+
+    if (threadIdx.x == 0) { q.ring_head = 0; q.ring_tail = 0; q.more_chunks = 1; }
+    __syncthreads();
 
     while (true) {
-        unsigned int chunk = 0;
-        if (lane == 0) chunk = atomicAdd(p.chunk_counter, 1u);
-        chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
-        if (chunk >= nchunks) break;
-
-        const int64_t mypix = (int64_t)chunk * 32 + lane;
-        bool mine = mypix < npix;
-        float mval = 0.0f;
-        if (mine) {
-            const int mx = (int)(mypix % p.W); const int64_t t = mypix / p.W;
-            mval = p.mask.ld1((int)(t / p.H), (int)(t % p.H), mx);
-        }
-        unsigned rem = __ballot_sync(0xFFFFFFFFu, mine && mval > 0.0f);
-        if (mine && !(mval > 0.0f)) {
-            // masked pixel: outputs are zero (the reference returns early on zero-initialised tensors, kernel.cu:478)
-            if (MODE != 1) {
-                float *d = p.diff + mypix * 3, *s = p.spec + mypix * 3;
-                d[0] = d[1] = d[2] = 0.0f; s[0] = s[1] = s[2] = 0.0f;
-            } else {
-                float *a = p.pos_grad + mypix * 3, *b = p.nrm_grad + mypix * 3, *c = p.kd_grad + mypix * 3, *d = p.ks_grad + mypix * 3;
-                a[0] = a[1] = a[2] = 0.0f; b[0] = b[1] = b[2] = 0.0f; c[0] = c[1] = c[2] = 0.0f; d[0] = d[1] = d[2] = 0.0f;
-            }
-        }
-
-        while (rem) {
-            // ---- take up to `group` active pixels of this chunk ----
-            int npx = 0;
-            __syncwarp();
-            while (npx < group && rem) {
-                const int src = __ffs(rem) - 1;
-                rem &= rem - 1;
-                if (lane == 0) q.pixid[npx] = (int)((int64_t)chunk * 32 + src);
-                ++npx;
-            }
-            __syncwarp();
-
-            // accumulators: only used across sub-chunks when one pixel needs several queue fills (items > QCAP)
-            f3 accD = F3(0.0f), accS = F3(0.0f);
-            f3 g_kd = F3(0.0f), g_ks = F3(0.0f), g_nrm = F3(0.0f), g_wo = F3(0.0f);
-
-            const int nsub = items <= QCAP ? 1 : (items + QCAP - 1) / QCAP;
-            for (int sub = 0; sub < nsub; ++sub) {
-                const int w0 = sub * QCAP, w1 = min(items, w0 + QCAP);
-                // ================= phase G =================
-                int qn = 0;
-                __syncwarp();
-#pragma unroll 1
-                for (int j = 0; j < npx; ++j) {
-                    const PixelIn px = load_pixel(p, (int64_t)q.pixid[j]);
-                    PixelFrame f;
-                    make_frame(px, f);
-                    if (lane < 3) {
-                        q.ro[j][lane] = lane == 0 ? px.ro.x : (lane == 1 ? px.ro.y : px.ro.z);
-                        q.wo[j][lane] = lane == 0 ? f.wo.x.v : (lane == 1 ? f.wo.y.v : f.wo.z.v);
+        // ---- collect active pixels: a few warps claim 32-pixel chunks until a full batch is waiting ----
+        while (true) {
+            const int have = q.ring_tail - q.ring_head;
+            const int more = q.more_chunks;
+            __syncthreads();
+            if (have >= NW || !more) break;
+            if (warp < 4) {
+                unsigned int chunk = 0;
+                if (lane == 0) chunk = atomicAdd(p.chunk_counter, 1u);
+                chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
+                if (chunk >= nchunks) { if (lane == 0) q.more_chunks = 0; }
+                else {
+                    const int64_t mypix = (int64_t)chunk * 32 + lane;
+                    const bool mine = mypix < npix;
+                    float mval = 0.0f;
+                    if (mine) {
+                        const int mx = (int)(mypix % p.W); const int64_t t = mypix / p.W;
+                        mval = p.mask.ld1((int)(t / p.H), (int)(t % p.H), mx);
                     }
-                    gen_segment<MODE>(p, q, qr, px, f, j, w0, w1, qn, lane);
-                    if (lane == 0) q.seg_end[j] = qn;
+                    const bool act = mine && mval > 0.0f;
+                    const unsigned am = __ballot_sync(0xFFFFFFFFu, act);
+                    if (mine && !act) {
+                        // masked pixel: outputs are zero (the reference returns early on zero-initialised tensors, kernel.cu:478)
+                        if (MODE != 1) {
+                            float *d = p.diff + mypix * 3, *s = p.spec + mypix * 3;
+                            d[0] = d[1] = d[2] = 0.0f; s[0] = s[1] = s[2] = 0.0f;
+                        } else {
+                            float *a = p.pos_grad + mypix * 3, *b = p.nrm_grad + mypix * 3, *c = p.kd_grad + mypix * 3, *d = p.ks_grad + mypix * 3;
+                            a[0] = a[1] = a[2] = 0.0f; b[0] = b[1] = b[2] = 0.0f; c[0] = c[1] = c[2] = 0.0f; d[0] = d[1] = d[2] = 0.0f;
+                        }
+                    }
+                    int base = 0;
+                    if (lane == 0 && am) base = atomicAdd(&q.ring_tail, __popc(am));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (act) q.pixring[(base + __popc(am & ((1u << lane) - 1u))) & (PIXRING - 1)] = (int)mypix;
                 }
-                __syncwarp();
-                // ================= phase T =================
-                if (trace_needed) trace_queue(p, q, qn, lane);        // sets tex bit 31 of occluded rays
+            }
+            __syncthreads();
+        }
+        const int have = q.ring_tail - q.ring_head;
+        if (have <= 0) break;
+        const int nb = have < NW ? have : NW;                 // pixels in this batch (one per warp)
+        const bool has_px = warp < nb;
+        const int64_t mypx = has_px ? (int64_t)q.pixring[(q.ring_head + warp) & (PIXRING - 1)] : 0;
+        __syncthreads();
+        if (threadIdx.x == 0) q.ring_head += nb;
+
+        // accumulators live across queue fills when one pixel needs several (items > SEG)
+        f3 accD = F3(0.0f), accS = F3(0.0f);
+        f3 g_kd = F3(0.0f), g_ks = F3(0.0f), g_nrm = F3(0.0f), g_wo = F3(0.0f);
+
+        for (int sub = 0; sub < nsub; ++sub) {
+            const int w0 = sub * SEG, w1 = min(items, w0 + SEG);
+            // ================= phase G =================
+            int qn = 0;
+            if (has_px) {
+                const PixelIn px = load_pixel(p, mypx);
+                PixelFrame f;
+                make_frame(px, f);
+                if (lane < 3) {
+                    q.ro[warp][lane] = lane == 0 ? px.ro.x : (lane == 1 ? px.ro.y : px.ro.z);
+                    q.wo[warp][lane] = lane == 0 ? f.wo.x.v : (lane == 1 ? f.wo.y.v : f.wo.z.v);
+                }
+                gen_segment<MODE>(p, q, qr, px, f, warp, w0, w1, qn, lane);
+            }
+            if (lane == 0) { q.seg_cnt[warp] = qn; q.seg_head[warp] = 0; q.pixid[warp] = (int)mypx; }
+            __syncthreads();
+            // ================= phase T =================
+            if (trace_needed) trace_queue(p, q, warp, lane);      // sets tex bit 31 of occluded rays
+            __syncthreads();
+            // ================= phase E =================
+            if (has_px) {
                 if (MODE == 2) {
                     for (int e = lane; e < qn; e += 32) {
-                        const size_t rec = (size_t)q.pixid[q.qpix[e]] * items + qr->slot[e];
-                        p.rec_vis[rec] = trace_needed ? (uint8_t)(1u - (q.tex[e] >> 31)) : (uint8_t)2;
+                        const size_t rec = (size_t)mypx * items + qr->slot[qb + e];
+                        p.rec_vis[rec] = trace_needed ? (uint8_t)(1u - (q.tex[qb + e] >> 31)) : (uint8_t)2;
                     }
                 }
-                // ================= phase E =================
-#pragma unroll 1
-                for (int j = 0; j < npx; ++j) {
-                    const int s0 = j ? q.seg_end[j - 1] : 0, s1 = q.seg_end[j];
-                    // dense list of entries with V != 0 (deterministic order)
-                    int vn = 0;
-                    for (int e0 = s0; e0 < s1; e0 += 32) {
-                        const int e = e0 + lane;
-                        const bool keep = e < s1 && (!(q.tex[e] >> 31) || v_occluded != 0.0f);
-                        const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
-                        if (keep) q.vlist[s0 + vn + __popc(m & ((1u << lane) - 1u))] = (uint16_t)e;
-                        vn += __popc(m);
-                    }
-                    __syncwarp();
-                    const PixelIn px = load_pixel(p, (int64_t)q.pixid[j]);
-                    const f3 wo_f = F3(q.wo[j][0], q.wo[j][1], q.wo[j][2]);
-                    f3 dgrad = F3(0.0f), sgrad = F3(0.0f);
-                    if (MODE == 1) { dgrad = p.diff_grad.ld3(px.iz, px.iy, px.ix); sgrad = p.spec_grad.ld3(px.iz, px.iy, px.ix); }
-                    if (nsub == 1) { accD = F3(0.0f); accS = F3(0.0f); g_kd = F3(0.0f); g_ks = F3(0.0f); g_nrm = F3(0.0f); g_wo = F3(0.0f); }
-
-                    for (int k = lane; k < vn; k += 32) {
-                        const int e = q.vlist[s0 + k];
-                        const f3 wi = F3(q.dx[e], q.dy[e], q.dz[e]);
-                        const uint32_t tex = q.tex[e];
-                        const int tx = tex & 0xFFFFu, ty = (tex >> 16) & 0x7FFFu;
-                        const float Vv = (tex >> 31) ? v_occluded : 1.0f;
-                        const float wgt = Vv * q.mis[e] * sample_frac;
-                        // process_sample, kernel.cu:403-461
-                        const float *lp = p.light + (size_t)ty * p.l_s1 + (size_t)tx * p.l_s2;
-                        const f3 light_col = F3(__ldg(lp), __ldg(lp + p.l_s3), __ldg(lp + 2 * p.l_s3));
-                        float diffv = 0.0f; f3 specv = F3(0.0f);
-                        if (diffuse_only) diffv = fwd_lambert(px.nrm, wi);
-                        else ox_fwd_pbr_bsdf(px.kd, px.ks, wo_f, px.nrm, wi, MIN_ROUGHNESS, diffv, specv);
-                        if (MODE != 1) {
-                            accD += light_col * (diffv * wgt);
-                            accS += specv * light_col * wgt;
-                        } else {
-                            // light gradient, kernel.cu:424-425 / 203-211
-                            const f3 lg = (dgrad * diffv + sgrad * specv) * wgt;
-                            float *gp = p.light_grad + ((size_t)ty * p.Wl + tx) * 3;
-                            if (lg.x != 0.0f) atomicAdd(gp, lg.x);
-                            if (lg.y != 0.0f) atomicAdd(gp + 1, lg.y);
-                            if (lg.z != 0.0f) atomicAdd(gp + 2, lg.z);
-                            const f3 dD = dgrad * light_col * wgt, dS = sgrad * light_col * wgt;
-                            if (diffuse_only) {
-                                f3 wi_grad = F3(0.0f);
-                                bwd_lambert(px.nrm, wi, g_nrm, wi_grad, sum(dD));
-                            } else {
-                                ox_bwd_pbr_bsdf(px.kd, px.ks, wo_f, px.nrm, wi, MIN_ROUGHNESS, g_kd, g_ks, g_wo, g_nrm, sum(dD), dS);
-                            }
-                        }
-                    }
-
-                    // ---- warp reduction, single writer per pixel (kernel.cu:442-456, 533-541) ----
-                    if (sub == nsub - 1) {
-                        if (MODE != 1) {
-                            float r0 = warp_sum(accD.x), r1 = warp_sum(accD.y), r2 = warp_sum(accD.z);
-                            float r3 = warp_sum(accS.x), r4 = warp_sum(accS.y), r5 = warp_sum(accS.z);
-                            if (lane == 0) {
-                                float *d = p.diff + px.pix * 3, *s = p.spec + px.pix * 3;
-                                d[0] = r0; d[1] = r1; d[2] = r2; s[0] = r3; s[1] = r4; s[2] = r5;
-                            }
-                        } else {
-                            f3 t_kd = F3(warp_sum(g_kd.x), warp_sum(g_kd.y), warp_sum(g_kd.z));
-                            f3 t_ks = F3(warp_sum(g_ks.x), warp_sum(g_ks.y), warp_sum(g_ks.z));
-                            f3 t_nrm = F3(warp_sum(g_nrm.x), warp_sum(g_nrm.y), warp_sum(g_nrm.z));
-                            f3 t_wo = F3(warp_sum(g_wo.x), warp_sum(g_wo.y), warp_sum(g_wo.z));
-                            if (lane == 0) {
-                                // wo = normalize(view_pos - pos): d_pos = -J^T d_wo (bsdf.h:270-274; d_view_pos is dropped, ops.py:105)
-                                f3 d__wo = F3(0.0f);
-                                bwd_safe_normalize(px.view - px.pos, d__wo, t_wo);
-                                float *a = p.pos_grad + px.pix * 3, *b = p.nrm_grad + px.pix * 3, *c = p.kd_grad + px.pix * 3, *d = p.ks_grad + px.pix * 3;
-                                a[0] = -d__wo.x; a[1] = -d__wo.y; a[2] = -d__wo.z;
-                                b[0] = t_nrm.x; b[1] = t_nrm.y; b[2] = t_nrm.z;
-                                c[0] = t_kd.x; c[1] = t_kd.y; c[2] = t_kd.z;
-                                d[0] = t_ks.x; d[1] = t_ks.y; d[2] = t_ks.z;
-                            }
-                        }
-                    }
+                // dense list of entries with V != 0 (deterministic order)
+                int vn = 0;
+                for (int e0 = 0; e0 < qn; e0 += 32) {
+                    const int e = e0 + lane;
+                    const bool keep = e < qn && (!(q.tex[qb + e] >> 31) || v_occluded != 0.0f);
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+                    if (keep) q.vlist[qb + vn + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(qb + e);
+                    vn += __popc(m);
                 }
                 __syncwarp();
+                const PixelIn px = load_pixel(p, mypx);
+                const f3 wo_f = F3(q.wo[warp][0], q.wo[warp][1], q.wo[warp][2]);
+                f3 dgrad = F3(0.0f), sgrad = F3(0.0f);
+                if (MODE == 1) { dgrad = p.diff_grad.ld3(px.iz, px.iy, px.ix); sgrad = p.spec_grad.ld3(px.iz, px.iy, px.ix); }
+
+                for (int k = lane; k < vn; k += 32) {
+                    const int e = q.vlist[qb + k];
+                    const f3 wi = F3(q.dx[e], q.dy[e], q.dz[e]);
+                    const uint32_t tex = q.tex[e];
+                    const int tx = tex & 0xFFFFu, ty = (tex >> 16) & 0x7FFFu;
+                    const float Vv = (tex >> 31) ? v_occluded : 1.0f;
+                    const float wgt = Vv * q.mis[e] * sample_frac;
+                    // process_sample, kernel.cu:403-461
+                    const float *lp = p.light + (size_t)ty * p.l_s1 + (size_t)tx * p.l_s2;
+                    const f3 light_col = F3(__ldg(lp), __ldg(lp + p.l_s3), __ldg(lp + 2 * p.l_s3));
+                    float diffv = 0.0f; f3 specv = F3(0.0f);
+                    if (diffuse_only) diffv = fwd_lambert(px.nrm, wi);
+                    else ox_fwd_pbr_bsdf(px.kd, px.ks, wo_f, px.nrm, wi, MIN_ROUGHNESS, diffv, specv);
+                    if (MODE != 1) {
+                        accD += light_col * (diffv * wgt);
+                        accS += specv * light_col * wgt;
+                    } else {
+                        // light gradient, kernel.cu:424-425 / 203-211
+                        const f3 lg = (dgrad * diffv + sgrad * specv) * wgt;
+                        float *gp = p.light_grad + ((size_t)ty * p.Wl + tx) * 3;
+                        if (lg.x != 0.0f) atomicAdd(gp, lg.x);
+                        if (lg.y != 0.0f) atomicAdd(gp + 1, lg.y);
+                        if (lg.z != 0.0f) atomicAdd(gp + 2, lg.z);
+                        const f3 dD = dgrad * light_col * wgt, dS = sgrad * light_col * wgt;
+                        if (diffuse_only) {
+                            f3 wi_grad = F3(0.0f);
+                            bwd_lambert(px.nrm, wi, g_nrm, wi_grad, sum(dD));
+                        } else {
+                            ox_bwd_pbr_bsdf(px.kd, px.ks, wo_f, px.nrm, wi, MIN_ROUGHNESS, g_kd, g_ks, g_wo, g_nrm, sum(dD), dS);
+                        }
+                    }
+                }
+
+                // ---- warp reduction, single writer per pixel (kernel.cu:442-456, 533-541) ----
+                if (sub == nsub - 1) {
+                    if (MODE != 1) {
+                        float r0 = warp_sum(accD.x), r1 = warp_sum(accD.y), r2 = warp_sum(accD.z);
+                        float r3 = warp_sum(accS.x), r4 = warp_sum(accS.y), r5 = warp_sum(accS.z);
+                        if (lane == 0) {
+                            float *d = p.diff + px.pix * 3, *s = p.spec + px.pix * 3;
+                            d[0] = r0; d[1] = r1; d[2] = r2; s[0] = r3; s[1] = r4; s[2] = r5;
+                        }
+                    } else {
+                        f3 t_kd = F3(warp_sum(g_kd.x), warp_sum(g_kd.y), warp_sum(g_kd.z));
+                        f3 t_ks = F3(warp_sum(g_ks.x), warp_sum(g_ks.y), warp_sum(g_ks.z));
+                        f3 t_nrm = F3(warp_sum(g_nrm.x), warp_sum(g_nrm.y), warp_sum(g_nrm.z));
+                        f3 t_wo = F3(warp_sum(g_wo.x), warp_sum(g_wo.y), warp_sum(g_wo.z));
+                        if (lane == 0) {
+                            // wo = normalize(view_pos - pos): d_pos = -J^T d_wo (bsdf.h:270-274; d_view_pos is dropped, ops.py:105)
+                            f3 d__wo = F3(0.0f);
+                            bwd_safe_normalize(px.view - px.pos, d__wo, t_wo);
+                            float *a = p.pos_grad + px.pix * 3, *b = p.nrm_grad + px.pix * 3, *c = p.kd_grad + px.pix * 3, *d = p.ks_grad + px.pix * 3;
+                            a[0] = -d__wo.x; a[1] = -d__wo.y; a[2] = -d__wo.z;
+                            b[0] = t_nrm.x; b[1] = t_nrm.y; b[2] = t_nrm.z;
+                            c[0] = t_kd.x; c[1] = t_kd.y; c[2] = t_kd.z;
+                            d[0] = t_ks.x; d[1] = t_ks.y; d[2] = t_ks.z;
+                        }
+                    }
+                }
             }
+            __syncthreads();
         }
     }
 }
@@ -746,7 +785,7 @@ static int fill_params(mcs_ctx *ctx, EnvParams &p,
     p.perms = (const int32_t *)perms->ptr; p.pm_s1 = perms->strides[1]; p.pm_s3 = perms->strides[3]; p.n_perms = (uint32_t)perms->sizes[1];
     p.m_rows = cdf_iters(p.Hl); p.m_cols = cdf_iters(p.Wl);
     p.bsdf = bsdf; p.seed = rnd_seed; p.batch_offset = batch_offset; p.shadow_scale = shadow_scale;
-    p.bvh = Bvh8View{(const float4 *)ctx->nodes8.p, (const float4 *)ctx->tris8.p};
+    p.bvh = BvhView{(const float4 *)ctx->nodes.p, (const float4 *)ctx->tris.p};
     if (int e = ensure_skip_table(ctx, p.N, s)) return e;
     p.skip = (const uint2 *)((const char *)ctx->lcg_skip.p);
     if (int e = mcs_buf_reserve(ctx->light_grad4, 256, s)) return e;
@@ -761,15 +800,15 @@ static int launch_env(const EnvParams &p, cudaStream_t s)
     int dev = 0, sms = 0, per_sm = 0;
     MCS_CUDA(cudaGetDevice(&dev));
     MCS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t smem = (sizeof(WarpQueue) + (MODE == 2 ? sizeof(WarpQueueRec) : 0)) * WARPS_PER_CTA;
+    const size_t smem = sizeof(BlockQueue) + (MODE == 2 ? sizeof(BlockQueueRec) : 0);
     MCS_CUDA(cudaFuncSetAttribute(env_shade_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, env_shade_kernel<MODE>, WARPS_PER_CTA * 32, smem));
+    MCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, env_shade_kernel<MODE>, NW * 32, smem));
     if (per_sm < 1) per_sm = 1;
     const int64_t npix = (int64_t)p.B * p.H * p.W;
-    int64_t want = (npix + 32 * WARPS_PER_CTA - 1) / (32 * WARPS_PER_CTA);
+    int64_t want = (npix + 32 * NW - 1) / (32 * NW);
     int grid = (int)(want < (int64_t)sms * per_sm ? want : (int64_t)sms * per_sm);
     if (grid < 1) grid = 1;
-    env_shade_kernel<MODE><<<grid, WARPS_PER_CTA * 32, smem, s>>>(p);
+    env_shade_kernel<MODE><<<grid, NW * 32, smem, s>>>(p);
     MCS_LAUNCH_CHECK();
     return 0;
 }
