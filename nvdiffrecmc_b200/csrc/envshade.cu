@@ -59,6 +59,9 @@ struct EnvParams {
     // fwd
     float *diff, *spec;
     int32_t *rec_texel; uint8_t *rec_vis;
+    uint32_t *hit_out;              // optional: per-pixel visibility record written by the forward pass
+    const uint32_t *hit_in;         // optional: record replayed by the backward pass instead of tracing
+    int hit_words;                  // uint32 words per pixel = ceil(2 N^2 / 32)
     // bwd
     TView diff_grad, spec_grad;
     float *pos_grad, *nrm_grad, *kd_grad, *ks_grad, *light_grad;
@@ -253,6 +256,9 @@ __device__ __forceinline__ float warp_sum(float v)
 //     drains it first and then steals from the other segments, so no lane idles while any ray of the batch is untraced.
 // Layout is SoA, conflict-free: lane k of a warp touches word k of a segment.  tex bit 31 = "occluded" flag (trace phase).
 // ---------------------------------------------------------------------------------------------
+#ifndef MCS_NEAR_FIRST
+#define MCS_NEAR_FIRST 1
+#endif
 #ifndef MCS_CTA_WARPS
 #define MCS_CTA_WARPS 32
 #endif
@@ -260,7 +266,7 @@ __device__ __forceinline__ float warp_sum(float v)
 #define MCS_LEAF_BATCH 32
 #endif
 #ifndef MCS_REFILL_BELOW
-#define MCS_REFILL_BELOW 24
+#define MCS_REFILL_BELOW 16
 #endif
 constexpr int NW = MCS_CTA_WARPS;
 constexpr int SEG = 128;                 // queue entries per warp segment (= one pixel at N = 8)
@@ -268,11 +274,14 @@ constexpr int QTOT = NW * SEG;
 constexpr int PCAP = 128;                // pending (ray, leaf) pairs per warp: < 32 carried over + at most 64 appended per node step
 constexpr int PIXRING = 256;
 static_assert(QTOT <= 65536, "queue entry index is stored in 16 bits");
+static_assert(SEG <= 256 && SEG % 32 == 0, "sample slot within a fill is stored in 8 bits");
 
 struct BlockQueue {
     float dx[QTOT], dy[QTOT], dz[QTOT], mis[QTOT];
     uint32_t tex[QTOT];
     uint16_t vlist[QTOT];                // per segment: dense list of entries that reach the eval phase
+    uint8_t qitem[QTOT];                 // sample slot of the entry within the current queue fill (w - w0 < SEG)
+    uint32_t hitw[NW][SEG / 32];         // per segment: occluded bits of the current queue fill
     uint16_t pl_ray[NW][PCAP];           // per warp: deferred leaf tests, queue entry ...
     int pl_leaf[NW][PCAP];               // ... and leaf code
     float ro[NW][3];                     // per segment: ray origin / view vector / pixel id / live-ray count / fetch cursor
@@ -403,6 +412,7 @@ __device__ __forceinline__ void gen_segment(const EnvParams &p, BlockQueue &q, B
             q.dx[e] = wi.x; q.dy[e] = wi.y; q.dz[e] = wi.z;
             q.mis[e] = 1.0f / fmaxf(pdf_sum, 0.0001f);          // MIS balance heuristic, kernel.cu:409
             q.tex[e] = (uint32_t)((ty << 16) | tx);
+            q.qitem[e] = (uint8_t)(w - w0);
             if (MODE == 2) qr->slot[e] = (uint32_t)(2 * i + (is_bsdf ? 1 : 0));
         }
         qn += __popc(m);
@@ -517,7 +527,11 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
                 hasB = h1 && ch1 < 0; leafB = ch1;
                 const bool i0 = h0 && ch0 >= 0, i1 = h1 && ch1 >= 0;
                 if (i0 && i1) {
+#if MCS_NEAR_FIRST
                     const bool first0 = tn0 <= tn1;        // nearer child first
+#else
+                    const bool first0 = true;
+#endif
                     stack[sp++] = first0 ? ch1 : ch0;
                     node = first0 ? ch0 : ch1;
                 } else if (i0) node = ch0;
@@ -588,6 +602,7 @@ __global__ void __launch_bounds__(NW * 32, 1) env_shade_kernel(const EnvParams p
                         if (MODE != 1) {
                             float *d = p.diff + mypix * 3, *s = p.spec + mypix * 3;
                             d[0] = d[1] = d[2] = 0.0f; s[0] = s[1] = s[2] = 0.0f;
+                            if (p.hit_out) for (int k = 0; k < p.hit_words; ++k) p.hit_out[(size_t)mypix * p.hit_words + k] = 0u;
                         } else {
                             float *a = p.pos_grad + mypix * 3, *b = p.nrm_grad + mypix * 3, *c = p.kd_grad + mypix * 3, *d = p.ks_grad + mypix * 3;
                             a[0] = a[1] = a[2] = 0.0f; b[0] = b[1] = b[2] = 0.0f; c[0] = c[1] = c[2] = 0.0f; d[0] = d[1] = d[2] = 0.0f;
@@ -630,8 +645,33 @@ __global__ void __launch_bounds__(NW * 32, 1) env_shade_kernel(const EnvParams p
             if (lane == 0) { q.seg_cnt[warp] = qn; q.seg_head[warp] = 0; q.pixid[warp] = (int)mypx; }
             __syncthreads();
             // ================= phase T =================
-            if (trace_needed) trace_queue(p, q, warp, lane);      // sets tex bit 31 of occluded rays
+            const bool replay = MODE == 1 && p.hit_in != nullptr;
+            if (replay) {
+                // backward with the forward pass's visibility record: no traversal at all
+                if (has_px) {
+                    if (lane < SEG / 32) {
+                        const int wi_ = w0 / 32 + lane;
+                        q.hitw[warp][lane] = wi_ < p.hit_words ? __ldg(p.hit_in + (size_t)mypx * p.hit_words + wi_) : 0u;
+                    }
+                    __syncwarp();
+                    for (int e = lane; e < qn; e += 32) {
+                        const int it = q.qitem[qb + e];
+                        if ((q.hitw[warp][it >> 5] >> (it & 31)) & 1u) q.tex[qb + e] |= 0x80000000u;
+                    }
+                }
+            } else if (trace_needed) trace_queue(p, q, warp, lane);      // sets tex bit 31 of occluded rays
             __syncthreads();
+            if (MODE != 1 && p.hit_out != nullptr && has_px) {
+                if (lane < SEG / 32) q.hitw[warp][lane] = 0u;
+                __syncwarp();
+                for (int e = lane; e < qn; e += 32)
+                    if (q.tex[qb + e] >> 31) { const int it = q.qitem[qb + e]; atomicOr(&q.hitw[warp][it >> 5], 1u << (it & 31)); }
+                __syncwarp();
+                if (lane < SEG / 32) {
+                    const int wi_ = w0 / 32 + lane;
+                    if (wi_ < p.hit_words) p.hit_out[(size_t)mypx * p.hit_words + wi_] = q.hitw[warp][lane];
+                }
+            }
             // ================= phase E =================
             if (has_px) {
                 if (MODE == 2) {
@@ -781,6 +821,7 @@ static int fill_params(mcs_ctx *ctx, EnvParams &p,
     p.rows = (const float *)rows->ptr; p.r_s = rows->strides[1];
     p.cols = (const float *)cols->ptr; p.c_s1 = cols->strides[1]; p.c_s2 = cols->strides[2];
     p.N = (int)n_samples_x; p.S = p.N * p.N;
+    p.hit_words = (2 * p.S + 31) / 32;
     MCS_REQUIRE(perms->sizes[3] == p.S && perms->sizes[1] >= 1, "env_shade: perms must be [P, n_samples_x^2]");
     p.perms = (const int32_t *)perms->ptr; p.pm_s1 = perms->strides[1]; p.pm_s3 = perms->strides[3]; p.n_perms = (uint32_t)perms->sizes[1];
     p.m_rows = cdf_iters(p.Hl); p.m_cols = cdf_iters(p.Wl);
@@ -823,14 +864,14 @@ int mcs_env_shade_fwd(mcs_ctx *ctx,
                       const mcs_tensor *light, const mcs_tensor *pdf, const mcs_tensor *rows, const mcs_tensor *cols,
                       const mcs_tensor *perms,
                       uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
-                      float *diff, float *spec, mcs_stream stream)
+                      float *diff, float *spec, uint32_t *hit_record, mcs_stream stream)
 {
     EnvParams p{};
     cudaStream_t s = (cudaStream_t)stream;
     if (int e = fill_params(ctx, p, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms, bsdf, n_samples_x, rnd_seed,
                             shadow_scale, batch_offset, s)) return e;
     MCS_REQUIRE(diff && spec, "env_shade_fwd: null output pointer");
-    p.diff = diff; p.spec = spec;
+    p.diff = diff; p.spec = spec; p.hit_out = hit_record;
     return launch_env<0>(p, s);
 }
 
@@ -859,7 +900,7 @@ int mcs_env_shade_bwd(mcs_ctx *ctx,
                       uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
                       const mcs_tensor *diff_grad, const mcs_tensor *spec_grad,
                       float *gb_pos_grad, float *gb_normal_grad, float *gb_kd_grad, float *gb_ks_grad, float *light_grad,
-                      mcs_stream stream)
+                      const uint32_t *hit_record, mcs_stream stream)
 {
     EnvParams p{};
     cudaStream_t s = (cudaStream_t)stream;
@@ -871,6 +912,7 @@ int mcs_env_shade_bwd(mcs_ctx *ctx,
         MCS_REQUIRE(diff_grad->sizes[d] == ro->sizes[d] && spec_grad->sizes[d] == ro->sizes[d], "env_shade_bwd: upstream gradient shape mismatch");
     p.diff_grad = make_view(diff_grad); p.spec_grad = make_view(spec_grad);
     p.pos_grad = gb_pos_grad; p.nrm_grad = gb_normal_grad; p.kd_grad = gb_kd_grad; p.ks_grad = gb_ks_grad; p.light_grad = light_grad;
+    p.hit_in = hit_record;
     MCS_CUDA(cudaMemsetAsync(light_grad, 0, sizeof(float) * 3 * (size_t)p.Hl * p.Wl, s));
     return launch_env<1>(p, s);
 }

@@ -12,6 +12,7 @@ import torch
 from .. import _lib as L
 
 _BSDF_MODES = ['pbr', 'diffuse', 'white']      # ops.py:136 -- order matters, it is the kernel's enum
+HIT_RECORD_REPLAY = True                        # backward replays the forward pass's visibility bits when the seed is shared
 
 
 def _f32(t, name):
@@ -32,6 +33,7 @@ class OptiXContext:
         L.check(L.lib().mcs_ctx_create(C.byref(h)), "mcs_ctx_create")
         self.cpp_wrapper = h
         self._geom = None        # keeps verts/tris alive: the build is asynchronous
+        self._version = 0        # bumped by every optix_build_bvh (guards the visibility-record replay)
 
     def __del__(self):
         try:
@@ -53,6 +55,7 @@ def optix_build_bvh(optix_ctx, verts, tris, rebuild):
         raise RuntimeError("tris must be int32 (the reference's callers do .int(), geometry/dlmesh.py:50)")
     t = tris.reshape(-1, 3).contiguous()
     optix_ctx._geom = (v, t)
+    optix_ctx._version += 1
     L.check(L.lib().mcs_bvh_build(optix_ctx.cpp_wrapper, v.data_ptr(), v.shape[0], t.data_ptr(), t.shape[0], int(rebuild), L.stream_ptr()),
             "optix_build_bvh")
 
@@ -92,10 +95,20 @@ class _optix_env_shade_func(torch.autograd.Function):
         B, H, W = ro.shape[0], ro.shape[1], ro.shape[2]
         diff = torch.empty(B, H, W, 3, dtype=torch.float32, device=ro.device)
         spec = torch.empty(B, H, W, 3, dtype=torch.float32, device=ro.device)
+        # Visibility record (1 bit per sample, 16 B/pixel at n_samples_x = 8): with a fixed seed the backward pass traces exactly the
+        # rays of the forward pass, so it can replay the record instead of re-tracing (the reference re-traces, torch_bindings.cpp:266).
+        # Not possible in decorrelated mode (rnd_seed=None draws a different seed for backward, ops.py:83,100).
+        need_grad = any(t.requires_grad for t in (gb_pos, gb_normal, gb_kd, gb_ks, light))
+        hit = None
+        if HIT_RECORD_REPLAY and rnd_seed is not None and need_grad:
+            hit = torch.empty(B, H, W, (2 * n_samples_x * n_samples_x + 31) // 32, dtype=torch.int32, device=ro.device)
         L.check(L.lib().mcs_env_shade_fwd(optix_ctx.cpp_wrapper, *[C.byref(x) for x in d], int(BSDF), int(n_samples_x),
                                           int(_rnd_seed) & 0xFFFFFFFF, float(shadow_scale), int(batch_offset),
-                                          diff.data_ptr(), spec.data_ptr(), L.stream_ptr()), "optix_env_shade (forward)")
+                                          diff.data_ptr(), spec.data_ptr(), hit.data_ptr() if hit is not None else None, L.stream_ptr()),
+                "optix_env_shade (forward)")
         ctx.save_for_backward(mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms)
+        ctx.hit = hit
+        ctx.bvh_version = optix_ctx._version
         ctx.optix_ctx = optix_ctx
         ctx.BSDF = BSDF
         ctx.n_samples_x = n_samples_x
@@ -116,10 +129,14 @@ class _optix_env_shade_func(torch.autograd.Function):
         g = [torch.empty(B, H, W, 3, dtype=torch.float32, device=dev) for _ in range(4)]
         light_grad = torch.empty(light.shape[0], light.shape[1], 3, dtype=torch.float32, device=dev)
         dg, sg = L.nhwc(diff_grad.float()), L.nhwc(spec_grad.float())
+        # replay is only valid against the acceleration structure the forward pass traced (the reference would re-trace whatever
+        # BVH the context holds at backward time); if the context was rebuilt in between, fall back to re-tracing
+        hit = ctx.hit if (ctx.hit is not None and ctx.bvh_version == optix_ctx._version) else None
         L.check(L.lib().mcs_env_shade_bwd(optix_ctx.cpp_wrapper, *[C.byref(x) for x in d], int(ctx.BSDF), int(ctx.n_samples_x),
                                           int(_rnd_seed) & 0xFFFFFFFF, float(ctx.shadow_scale), int(ctx.batch_offset),
                                           C.byref(dg), C.byref(sg), g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), g[3].data_ptr(),
-                                          light_grad.data_ptr(), L.stream_ptr()), "optix_env_shade (backward)")
+                                          light_grad.data_ptr(), hit.data_ptr() if hit is not None else None, L.stream_ptr()),
+                "optix_env_shade (backward)")
         # same gradient slots as ops.py:105 (no gradient for ro / view_pos / pdf / rows / cols)
         return (None, None, None, g[0], g[1], None, g[2], g[3], light_grad, None, None, None, None, None, None, None, None, None)
 

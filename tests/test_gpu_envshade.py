@@ -130,3 +130,63 @@ def test_errors_are_loud(dev):
         ou.optix_build_bvh(ctx, torch.zeros(3, 3, device=dev), torch.zeros(0, 3, dtype=torch.int32, device=dev), 1)
     with pytest.raises(RuntimeError, match="CUDA tensors"):
         ou.optix_build_bvh(ctx, torch.zeros(3, 3), torch.zeros(1, 3, dtype=torch.int32), 1)
+
+
+def test_backward_replays_the_visibility_record(dev):
+    """With a shared seed the backward pass replays the forward pass's hit record instead of re-tracing; both must agree
+    (identical rays, identical bits; only the light-gradient atomics reorder)."""
+    import nvdiffrecmc_b200.optixutils as ou
+    from nvdiffrecmc_b200.optixutils import ops
+    N = 4
+    c = make_case(res=20, B=2, N=N, seed=7)
+    ctx = _ctx(c, dev)
+    perms = _t(c, "perms", dev)
+    grads = {}
+    for replay in (True, False):
+        ops.HIT_RECORD_REPLAY = replay
+        try:
+            mask, ro, pos, nrm, view, kd, ks, light, pdf, rows, cols = _args(c, dev)
+            for x in (pos, nrm, kd, ks, light):
+                x.requires_grad_(True)
+            d, s = ou.optix_env_shade(ctx, mask, ro, pos, nrm, view, kd, ks, light, pdf, rows, cols, n_samples_x=N, rnd_seed=21, perms=perms)
+            (d.sum() * 0.7 + (s * s).sum()).backward()
+            grads[replay] = [x.grad.clone() for x in (pos, nrm, kd, ks, light)]
+        finally:
+            ops.HIT_RECORD_REPLAY = True
+    for a, b in zip(grads[True][:4], grads[False][:4]):
+        assert torch.equal(a, b)
+    assert rel_l2(grads[True][4].cpu().numpy(), grads[False][4].cpu().numpy()) < 1e-6
+    # a context rebuilt between forward and backward invalidates the record: the op falls back to re-tracing (no stale replay)
+    mask, ro, pos, nrm, view, kd, ks, light, pdf, rows, cols = _args(c, dev)
+    light.requires_grad_(True)
+    d, s = ou.optix_env_shade(ctx, mask, ro, pos, nrm, view, kd, ks, light, pdf, rows, cols, n_samples_x=N, rnd_seed=21, perms=perms)
+    ou.optix_build_bvh(ctx, _t(c, "verts", dev), _t(c, "tris", dev), rebuild=1)
+    (d.sum() + s.sum()).backward()
+    assert torch.isfinite(light.grad).all()
+
+
+def test_decorrelated_mode_and_multi_fill_pixels(dev):
+    """rnd_seed=None draws independent seeds for forward and backward (ops.py:83,100: no replay possible); n_samples_x=9 needs two
+    queue fills per pixel (162 sample slots > 128)."""
+    import nvdiffrecmc_b200.optixutils as ou
+    N = 9
+    c = make_case(res=12, B=1, N=N, seed=8, perm_rows=64)
+    ctx = _ctx(c, dev)
+    mask, ro, pos, nrm, view, kd, ks, light, pdf, rows, cols = _args(c, dev)
+    for x in (kd, light):
+        x.requires_grad_(True)
+    perms = _t(c, "perms", dev)
+    d, s = ou.optix_env_shade(ctx, mask, ro, pos, nrm, view, kd, ks, light, pdf, rows, cols, n_samples_x=N, rnd_seed=4, perms=perms)
+    o = oracle()
+    d_ref, s_ref = o.env_shade(c["scene"], c["mask"], c["ro"], c["pos"], c["nrm"], c["view"], c["kd"], c["ks"], c["light"], c["pdf"], c["rows"],
+                               c["cols"], c["perms"], n_samples_x=N, rnd_seed=4)
+    assert rel_l2(d.detach().cpu().numpy(), d_ref) < TOL and rel_l2(s.detach().cpu().numpy(), s_ref) < TOL
+    dg = np.random.default_rng(1).uniform(0, 1, size=d.shape).astype(np.float32)
+    torch.autograd.backward([d, s], [torch.tensor(dg, device=dev), torch.tensor(dg, device=dev)])
+    ref = o.env_shade(c["scene"], c["mask"], c["ro"], c["pos"], c["nrm"], c["view"], c["kd"], c["ks"], c["light"], c["pdf"], c["rows"], c["cols"],
+                      c["perms"], n_samples_x=N, rnd_seed=4, grads=(dg, dg))
+    assert rel_l2(kd.grad.cpu().numpy(), ref[2]) < TOL and rel_l2(light.grad.cpu().numpy(), ref[4]) < TOL
+    np.random.seed(0)
+    d2, s2 = ou.optix_env_shade(ctx, mask, ro, pos, nrm, view, kd, ks, light, pdf, rows, cols, n_samples_x=N, rnd_seed=None, perms=perms)
+    (d2.sum() + s2.sum()).backward()
+    assert torch.isfinite(d2).all() and torch.isfinite(light.grad).all()
