@@ -16,8 +16,11 @@
 //   5. leaves+refit: padded leaf boxes, sorted triangle records (v0,e1,e2 as 3 x float4), bottom-up
 //                    box union with arrival counters (second thread to arrive continues)
 //   6. emit        : 64-byte binary traversal nodes (closest-hit queries) holding both children's boxes
-//   7. build_wide  : collapse into the 8-wide compressed layout walked by the shadow rays (bvh8.cuh)
+//   7. build_wide  : (MCS_BVH8=1 only) collapse into the 8-wide compressed layout of bvh8.cuh -- a measured experiment, not the default
 #include <cub/cub.cuh>
+#ifndef MCS_BVH8
+#define MCS_BVH8 0      // 1: also build the 8-wide compressed layout (bvh8.cuh) and use it for mcs_trace_visibility (experiment)
+#endif
 #include "bvh8.cuh"
 #include "ctx.h"
 
@@ -351,12 +354,21 @@ __global__ void __launch_bounds__(1024) k_build_wide(int T, const int32_t *__res
     }
 }
 
-__global__ void __launch_bounds__(128) k_visibility(Bvh8View b, const float *__restrict__ ro, const float *__restrict__ rd, int64_t n, uint8_t *__restrict__ vis)
+#if MCS_BVH8
+typedef Bvh8View VisView;
+#else
+typedef BvhView VisView;
+#endif
+__global__ void __launch_bounds__(128) k_visibility(VisView b, const float *__restrict__ ro, const float *__restrict__ rd, int64_t n, uint8_t *__restrict__ vis)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     f3 o = F3(ro[3 * i], ro[3 * i + 1], ro[3 * i + 2]), d = F3(rd[3 * i], rd[3 * i + 1], rd[3 * i + 2]);
-    vis[i] = bvh8_occluded(b, o, d) ? 0 : 1;       // same 8-wide structure the fused env_shade kernel walks
+#if MCS_BVH8
+    vis[i] = bvh8_occluded(b, o, d) ? 0 : 1;
+#else
+    vis[i] = bvh_occluded(b, o, d) ? 0 : 1;        // same nodes, triangles and predicate as the fused env_shade kernel
+#endif
 }
 
 __global__ void __launch_bounds__(128) k_closest(BvhView b, const float *__restrict__ ro, const float *__restrict__ rd, int64_t n,
@@ -423,9 +435,11 @@ int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris
     if (int e = mcs_buf_reserve(c->range, nT * sizeof(int2), s)) return e;
     if (int e = mcs_buf_reserve(c->nodes, nT * 4 * sizeof(float4), s)) return e;
     if (int e = mcs_buf_reserve(c->tris, nT * 3 * sizeof(float4), s)) return e;
+#if MCS_BVH8
     if (int e = mcs_buf_reserve(c->nodes8, nT * 5 * sizeof(float4), s)) return e;
     if (int e = mcs_buf_reserve(c->tris8, nT * 3 * sizeof(float4), s)) return e;
     if (int e = mcs_buf_reserve(c->wide_bin, nT * sizeof(int), s)) return e;
+#endif
 
     uint32_t *bounds = (uint32_t *)c->bounds.p;
     float *tlo = (float *)c->tlo.p, *thi = (float *)c->thi.p;
@@ -455,9 +469,11 @@ int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris
     k_emit_nodes<<<nblk(T > 1 ? T - 1 : 1, 256), 256, 0, s>>>(T, (const int32_t *)c->left.p, (const int32_t *)c->right.p, (const int2 *)c->range.p,
                                                               (const float *)c->lo.p, (const float *)c->hi.p, (float4 *)c->nodes.p);
     MCS_LAUNCH_CHECK();
+#if MCS_BVH8
     k_build_wide<<<1, 1024, 0, s>>>(T, (const int32_t *)c->left.p, (const int32_t *)c->right.p, (const int2 *)c->range.p, (const float *)c->lo.p,
                                     (const float *)c->hi.p, (const float4 *)c->tris.p, (float4 *)c->nodes8.p, (float4 *)c->tris8.p, (int *)c->wide_bin.p);
     MCS_LAUNCH_CHECK();
+#endif
     c->T = T; c->V = V;
     return 0;
 }
@@ -483,7 +499,11 @@ int mcs_trace_visibility(mcs_ctx *c, const float *ro, const float *rd, int64_t n
     MCS_REQUIRE(c && c->T > 0, "mcs_trace_visibility: no acceleration structure built (call mcs_bvh_build first)");
     MCS_REQUIRE(n >= 0 && (n == 0 || (ro && rd && vis)), "mcs_trace_visibility: bad arguments");
     if (n == 0) return 0;
-    Bvh8View b{(const float4 *)c->nodes8.p, (const float4 *)c->tris8.p};
+#if MCS_BVH8
+    VisView b{(const float4 *)c->nodes8.p, (const float4 *)c->tris8.p};
+#else
+    VisView b{(const float4 *)c->nodes.p, (const float4 *)c->tris.p};
+#endif
     k_visibility<<<nblk(n, 128), 128, 0, (cudaStream_t)stream>>>(b, ro, rd, n, vis);
     MCS_LAUNCH_CHECK();
     return 0;

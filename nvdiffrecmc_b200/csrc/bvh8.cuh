@@ -1,4 +1,7 @@
-// bvh8.cuh -- 8-wide compressed BVH (CWBVH-style, Ylitie/Karras/Laine 2017) used by the shadow rays.
+// bvh8.cuh -- 8-wide compressed BVH (CWBVH-style, Ylitie/Karras/Laine 2017).  EXPERIMENT, off by default (MCS_BVH8=0):
+// bit-exact and parity-green, but on B200 the fused kernel was 15 % slower with it than with binary nodes + deferred leaf
+// tests (profiles/r01_bvh8_envshade_summary.json: long-scoreboard stalls fell from 35 % to 13 % as intended, but the 600-
+// instruction node test made 45 % of the stall samples instruction-fetch misses).  Kept for round 2 (rolled child loop).
 //
 // Why (profiles/r01_v3_*): with 64-byte binary nodes the node array of even a 7k-triangle mesh (460 KB)
 // does not fit in L1; the trace loop's top stall was the L2 round trip of every node fetch (long
