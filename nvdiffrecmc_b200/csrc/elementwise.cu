@@ -34,10 +34,12 @@ __device__ __forceinline__ void px_decode(const Grid &g, int64_t p, int &n, int 
     n = (int)(t / g.H);
 }
 
-template <int C>
+// FULL = all four pixels valid: every loop bound and array index is a compile-time constant, so the pixel
+// registers never spill to local memory (the ragged tail is a separate, rarely executed instantiation).
+template <int C, bool FULL>
 __device__ __forceinline__ void ew_load(const TIn &t, const Grid &g, const Px4 &q, float (&out)[4][C])
 {
-    if (t.fast && q.cnt == 4) {
+    if (FULL && t.fast) {
         const float4 *src = reinterpret_cast<const float4 *>(t.v.p + q.p0 * C);
         float buf[4 * C];
 #pragma unroll
@@ -52,7 +54,7 @@ __device__ __forceinline__ void ew_load(const TIn &t, const Grid &g, const Px4 &
     } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (k < q.cnt) {
+            if (FULL || k < q.cnt) {
                 int n, h, w;
                 px_decode(g, q.p0 + k, n, h, w);
                 const float *src = t.v.p + t.v.off(n, h, w);
@@ -66,10 +68,10 @@ __device__ __forceinline__ void ew_load(const TIn &t, const Grid &g, const Px4 &
     }
 }
 
-template <int C>
+template <int C, bool FULL>
 __device__ __forceinline__ void ew_store(float *dst, const Px4 &q, const float (&v)[4][C])
 {
-    if (q.cnt == 4) {
+    if (FULL) {
         float buf[4 * C];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -79,9 +81,12 @@ __device__ __forceinline__ void ew_store(float *dst, const Px4 &q, const float (
 #pragma unroll
         for (int i = 0; i < C; ++i) d[i] = make_float4(buf[4 * i], buf[4 * i + 1], buf[4 * i + 2], buf[4 * i + 3]);
     } else {
-        for (int k = 0; k < q.cnt; ++k)
 #pragma unroll
-            for (int c = 0; c < C; ++c) dst[(q.p0 + k) * C + c] = v[k][c];
+        for (int k = 0; k < 4; ++k)
+            if (k < q.cnt) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) dst[(q.p0 + k) * C + c] = v[k][c];
+            }
     }
 }
 
@@ -97,7 +102,8 @@ __global__ void __launch_bounds__(256) ew_kernel(Op op, Grid g)
     if (q.p0 >= g.npx) return;
     int64_t rem = g.npx - q.p0;
     q.cnt = rem >= 4 ? 4 : (int)rem;
-    op.run(g, q);
+    if (q.cnt == 4) op.template run<true>(g, q);
+    else op.template run<false>(g, q);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -105,101 +111,101 @@ __global__ void __launch_bounds__(256) ew_kernel(Op op, Grid g)
 // ---------------------------------------------------------------------------------------------
 struct LambertFwd {
     TIn nrm, wi; float *out;
-    __device__ void run(const Grid &g, const Px4 &q) const
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
     {
         float a[4][3], b[4][3], o[4][1];
-        ew_load<3>(nrm, g, q, a); ew_load<3>(wi, g, q, b);
+        ew_load<3, FULL>(nrm, g, q, a); ew_load<3, FULL>(wi, g, q, b);
 #pragma unroll
         for (int k = 0; k < 4; ++k) o[k][0] = fwd_lambert(to3(a[k]), to3(b[k]));
-        ew_store<1>(out, q, o);
+        ew_store<1, FULL>(out, q, o);
     }
 };
 struct LambertBwd {
     TIn nrm, wi, dout; float *d_nrm, *d_wi;
-    __device__ void run(const Grid &g, const Px4 &q) const
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
     {
         float a[4][3], b[4][3], d[4][1], ga[4][3], gb[4][3];
-        ew_load<3>(nrm, g, q, a); ew_load<3>(wi, g, q, b); ew_load<1>(dout, g, q, d);
+        ew_load<3, FULL>(nrm, g, q, a); ew_load<3, FULL>(wi, g, q, b); ew_load<1, FULL>(dout, g, q, d);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             f3 x = F3(0.0f), y = F3(0.0f);
             bwd_lambert(to3(a[k]), to3(b[k]), x, y, d[k][0]);
             from3(ga[k], x); from3(gb[k], y);
         }
-        ew_store<3>(d_nrm, q, ga); ew_store<3>(d_wi, q, gb);
+        ew_store<3, FULL>(d_nrm, q, ga); ew_store<3, FULL>(d_wi, q, gb);
     }
 };
 struct FrostbiteFwd {
     TIn nrm, wi, wo, lr; float *out;
-    __device__ void run(const Grid &g, const Px4 &q) const
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
     {
         float a[4][3], b[4][3], c[4][3], l[4][1], o[4][1];
-        ew_load<3>(nrm, g, q, a); ew_load<3>(wi, g, q, b); ew_load<3>(wo, g, q, c); ew_load<1>(lr, g, q, l);
+        ew_load<3, FULL>(nrm, g, q, a); ew_load<3, FULL>(wi, g, q, b); ew_load<3, FULL>(wo, g, q, c); ew_load<1, FULL>(lr, g, q, l);
 #pragma unroll
         for (int k = 0; k < 4; ++k) o[k][0] = fwd_frostbite(to3(a[k]), to3(b[k]), to3(c[k]), l[k][0]);
-        ew_store<1>(out, q, o);
+        ew_store<1, FULL>(out, q, o);
     }
 };
 struct FrostbiteBwd {
     TIn nrm, wi, wo, lr, dout; float *d_nrm, *d_wi, *d_wo, *d_lr;
-    __device__ void run(const Grid &g, const Px4 &q) const
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
     {
         float a[4][3], b[4][3], c[4][3], l[4][1], d[4][1], ga[4][3], gb[4][3], gc[4][3], gl[4][1];
-        ew_load<3>(nrm, g, q, a); ew_load<3>(wi, g, q, b); ew_load<3>(wo, g, q, c); ew_load<1>(lr, g, q, l); ew_load<1>(dout, g, q, d);
+        ew_load<3, FULL>(nrm, g, q, a); ew_load<3, FULL>(wi, g, q, b); ew_load<3, FULL>(wo, g, q, c); ew_load<1, FULL>(lr, g, q, l); ew_load<1, FULL>(dout, g, q, d);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             f3 x = F3(0.0f), y = F3(0.0f), z = F3(0.0f); float dl = 0.0f;
             bwd_frostbite(to3(a[k]), to3(b[k]), to3(c[k]), l[k][0], x, y, z, dl, d[k][0]);
             from3(ga[k], x); from3(gb[k], y); from3(gc[k], z); gl[k][0] = dl;
         }
-        ew_store<3>(d_nrm, q, ga); ew_store<3>(d_wi, q, gb); ew_store<3>(d_wo, q, gc); ew_store<1>(d_lr, q, gl);
+        ew_store<3, FULL>(d_nrm, q, ga); ew_store<3, FULL>(d_wi, q, gb); ew_store<3, FULL>(d_wo, q, gc); ew_store<1, FULL>(d_lr, q, gl);
     }
 };
 struct FresnelFwd {
     TIn f0, f90, c; float *out;
-    __device__ void run(const Grid &g, const Px4 &q) const
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
     {
         float a[4][3], b[4][3], cc[4][1], o[4][3];
-        ew_load<3>(f0, g, q, a); ew_load<3>(f90, g, q, b); ew_load<1>(c, g, q, cc);
+        ew_load<3, FULL>(f0, g, q, a); ew_load<3, FULL>(f90, g, q, b); ew_load<1, FULL>(c, g, q, cc);
 #pragma unroll
         for (int k = 0; k < 4; ++k) from3(o[k], fwd_fresnel3(to3(a[k]), to3(b[k]), cc[k][0]));
-        ew_store<3>(out, q, o);
+        ew_store<3, FULL>(out, q, o);
     }
 };
 struct FresnelBwd {
     TIn f0, f90, c, dout; float *d_f0, *d_f90, *d_c;
-    __device__ void run(const Grid &g, const Px4 &q) const
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
     {
         float a[4][3], b[4][3], cc[4][1], d[4][3], ga[4][3], gb[4][3], gc[4][1];
-        ew_load<3>(f0, g, q, a); ew_load<3>(f90, g, q, b); ew_load<1>(c, g, q, cc); ew_load<3>(dout, g, q, d);
+        ew_load<3, FULL>(f0, g, q, a); ew_load<3, FULL>(f90, g, q, b); ew_load<1, FULL>(c, g, q, cc); ew_load<3, FULL>(dout, g, q, d);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             f3 x = F3(0.0f), y = F3(0.0f); float z = 0.0f;
             bwd_fresnel3(to3(a[k]), to3(b[k]), cc[k][0], x, y, z, to3(d[k]));
             from3(ga[k], x); from3(gb[k], y); gc[k][0] = z;
         }
-        ew_store<3>(d_f0, q, ga); ew_store<3>(d_f90, q, gb); ew_store<1>(d_c, q, gc);
+        ew_store<3, FULL>(d_f0, q, ga); ew_store<3, FULL>(d_f90, q, gb); ew_store<1, FULL>(d_c, q, gc);
     }
 };
 template <int WHICH>   // 0 ndf, 1 lambda
 struct Ggx2Fwd {
     TIn a2, c; float *out;
-    __device__ void run(const Grid &g, const Px4 &q) const
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
     {
         float a[4][1], b[4][1], o[4][1];
-        ew_load<1>(a2, g, q, a); ew_load<1>(c, g, q, b);
+        ew_load<1, FULL>(a2, g, q, a); ew_load<1, FULL>(c, g, q, b);
 #pragma unroll
         for (int k = 0; k < 4; ++k) o[k][0] = WHICH == 0 ? fwd_ndf_ggx(a[k][0], b[k][0]) : fwd_lambda_ggx(a[k][0], b[k][0]);
-        ew_store<1>(out, q, o);
+        ew_store<1, FULL>(out, q, o);
     }
 };
 template <int WHICH>
 struct Ggx2Bwd {
     TIn a2, c, dout; float *d_a2, *d_c;
-    __device__ void run(const Grid &g, const Px4 &q) const
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
     {
         float a[4][1], b[4][1], d[4][1], ga[4][1], gb[4][1];
-        ew_load<1>(a2, g, q, a); ew_load<1>(c, g, q, b); ew_load<1>(dout, g, q, d);
+        ew_load<1, FULL>(a2, g, q, a); ew_load<1, FULL>(c, g, q, b); ew_load<1, FULL>(dout, g, q, d);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             float x = 0.0f, y = 0.0f;
@@ -207,53 +213,53 @@ struct Ggx2Bwd {
             else bwd_lambda_ggx(a[k][0], b[k][0], x, y, d[k][0]);
             ga[k][0] = x; gb[k][0] = y;
         }
-        ew_store<1>(d_a2, q, ga); ew_store<1>(d_c, q, gb);
+        ew_store<1, FULL>(d_a2, q, ga); ew_store<1, FULL>(d_c, q, gb);
     }
 };
 struct MaskingFwd {
     TIn a2, ci, co; float *out;
-    __device__ void run(const Grid &g, const Px4 &q) const
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
     {
         float a[4][1], b[4][1], c[4][1], o[4][1];
-        ew_load<1>(a2, g, q, a); ew_load<1>(ci, g, q, b); ew_load<1>(co, g, q, c);
+        ew_load<1, FULL>(a2, g, q, a); ew_load<1, FULL>(ci, g, q, b); ew_load<1, FULL>(co, g, q, c);
 #pragma unroll
         for (int k = 0; k < 4; ++k) o[k][0] = fwd_masking_smith(a[k][0], b[k][0], c[k][0]);
-        ew_store<1>(out, q, o);
+        ew_store<1, FULL>(out, q, o);
     }
 };
 struct MaskingBwd {
     TIn a2, ci, co, dout; float *d_a2, *d_ci, *d_co;
-    __device__ void run(const Grid &g, const Px4 &q) const
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
     {
         float a[4][1], b[4][1], c[4][1], d[4][1], ga[4][1], gb[4][1], gc[4][1];
-        ew_load<1>(a2, g, q, a); ew_load<1>(ci, g, q, b); ew_load<1>(co, g, q, c); ew_load<1>(dout, g, q, d);
+        ew_load<1, FULL>(a2, g, q, a); ew_load<1, FULL>(ci, g, q, b); ew_load<1, FULL>(co, g, q, c); ew_load<1, FULL>(dout, g, q, d);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             float x = 0.0f, y = 0.0f, z = 0.0f;
             bwd_masking_smith(a[k][0], b[k][0], c[k][0], x, y, z, d[k][0]);
             ga[k][0] = x; gb[k][0] = y; gc[k][0] = z;
         }
-        ew_store<1>(d_a2, q, ga); ew_store<1>(d_ci, q, gb); ew_store<1>(d_co, q, gc);
+        ew_store<1, FULL>(d_a2, q, ga); ew_store<1, FULL>(d_ci, q, gb); ew_store<1, FULL>(d_co, q, gc);
     }
 };
 struct SpecFwd {
     TIn col, nrm, wo, wi, alpha; float min_roughness; float *out;
-    __device__ void run(const Grid &g, const Px4 &q) const
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
     {
         float a[4][3], b[4][3], c[4][3], d[4][3], al[4][1], o[4][3];
-        ew_load<3>(col, g, q, a); ew_load<3>(nrm, g, q, b); ew_load<3>(wo, g, q, c); ew_load<3>(wi, g, q, d); ew_load<1>(alpha, g, q, al);
+        ew_load<3, FULL>(col, g, q, a); ew_load<3, FULL>(nrm, g, q, b); ew_load<3, FULL>(wo, g, q, c); ew_load<3, FULL>(wi, g, q, d); ew_load<1, FULL>(alpha, g, q, al);
 #pragma unroll
         for (int k = 0; k < 4; ++k) from3(o[k], fwd_pbr_specular(to3(a[k]), to3(b[k]), to3(c[k]), to3(d[k]), al[k][0], min_roughness));
-        ew_store<3>(out, q, o);
+        ew_store<3, FULL>(out, q, o);
     }
 };
 struct SpecBwd {
     TIn col, nrm, wo, wi, alpha, dout; float min_roughness; float *d_col, *d_nrm, *d_wo, *d_wi, *d_alpha;
-    __device__ void run(const Grid &g, const Px4 &q) const
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
     {
         float a[4][3], b[4][3], c[4][3], d[4][3], al[4][1], go[4][3];
-        ew_load<3>(col, g, q, a); ew_load<3>(nrm, g, q, b); ew_load<3>(wo, g, q, c); ew_load<3>(wi, g, q, d); ew_load<1>(alpha, g, q, al);
-        ew_load<3>(dout, g, q, go);
+        ew_load<3, FULL>(col, g, q, a); ew_load<3, FULL>(nrm, g, q, b); ew_load<3, FULL>(wo, g, q, c); ew_load<3, FULL>(wi, g, q, d); ew_load<1, FULL>(alpha, g, q, al);
+        ew_load<3, FULL>(dout, g, q, go);
         float ga[4][3], gb[4][3], gc[4][3], gd[4][3], gal[4][1];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -261,30 +267,30 @@ struct SpecBwd {
             bwd_pbr_specular(to3(a[k]), to3(b[k]), to3(c[k]), to3(d[k]), al[k][0], min_roughness, x, y, z, w, da, to3(go[k]));
             from3(ga[k], x); from3(gb[k], y); from3(gc[k], z); from3(gd[k], w); gal[k][0] = da;
         }
-        ew_store<3>(d_col, q, ga); ew_store<3>(d_nrm, q, gb); ew_store<3>(d_wo, q, gc); ew_store<3>(d_wi, q, gd); ew_store<1>(d_alpha, q, gal);
+        ew_store<3, FULL>(d_col, q, ga); ew_store<3, FULL>(d_nrm, q, gb); ew_store<3, FULL>(d_wo, q, gc); ew_store<3, FULL>(d_wi, q, gd); ew_store<1, FULL>(d_alpha, q, gal);
     }
 };
 struct PbrFwd {
     TIn kd, arm, pos, nrm, view, light; float min_roughness; int bsdf; float *out;
-    __device__ void run(const Grid &g, const Px4 &q) const
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
     {
         float a[4][3], b[4][3], c[4][3], d[4][3], e[4][3], f[4][3], o[4][3];
-        ew_load<3>(kd, g, q, a); ew_load<3>(arm, g, q, b); ew_load<3>(pos, g, q, c);
-        ew_load<3>(nrm, g, q, d); ew_load<3>(view, g, q, e); ew_load<3>(light, g, q, f);
+        ew_load<3, FULL>(kd, g, q, a); ew_load<3, FULL>(arm, g, q, b); ew_load<3, FULL>(pos, g, q, c);
+        ew_load<3, FULL>(nrm, g, q, d); ew_load<3, FULL>(view, g, q, e); ew_load<3, FULL>(light, g, q, f);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             from3(o[k], ru_fwd_pbr_bsdf(to3(a[k]), to3(b[k]), to3(c[k]), to3(d[k]), to3(e[k]), to3(f[k]), min_roughness, bsdf));
-        ew_store<3>(out, q, o);
+        ew_store<3, FULL>(out, q, o);
     }
 };
 struct PbrBwd {
     TIn kd, arm, pos, nrm, view, light, dout; float min_roughness; int bsdf;
     float *d_kd, *d_arm, *d_pos, *d_nrm, *d_view, *d_light;
-    __device__ void run(const Grid &g, const Px4 &q) const
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
     {
         float a[4][3], b[4][3], c[4][3], d[4][3], e[4][3], f[4][3], go[4][3];
-        ew_load<3>(kd, g, q, a); ew_load<3>(arm, g, q, b); ew_load<3>(pos, g, q, c);
-        ew_load<3>(nrm, g, q, d); ew_load<3>(view, g, q, e); ew_load<3>(light, g, q, f); ew_load<3>(dout, g, q, go);
+        ew_load<3, FULL>(kd, g, q, a); ew_load<3, FULL>(arm, g, q, b); ew_load<3, FULL>(pos, g, q, c);
+        ew_load<3, FULL>(nrm, g, q, d); ew_load<3, FULL>(view, g, q, e); ew_load<3, FULL>(light, g, q, f); ew_load<3, FULL>(dout, g, q, go);
         float ga[4][3], gb[4][3], gc[4][3], gd[4][3], ge[4][3], gf[4][3];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -293,17 +299,17 @@ struct PbrBwd {
                             x0, x1, x2, x3, x4, x5, to3(go[k]));
             from3(ga[k], x0); from3(gb[k], x1); from3(gc[k], x2); from3(gd[k], x3); from3(ge[k], x4); from3(gf[k], x5);
         }
-        ew_store<3>(d_kd, q, ga); ew_store<3>(d_arm, q, gb); ew_store<3>(d_pos, q, gc);
-        ew_store<3>(d_nrm, q, gd); ew_store<3>(d_view, q, ge); ew_store<3>(d_light, q, gf);
+        ew_store<3, FULL>(d_kd, q, ga); ew_store<3, FULL>(d_arm, q, gb); ew_store<3, FULL>(d_pos, q, gc);
+        ew_store<3, FULL>(d_nrm, q, gd); ew_store<3, FULL>(d_view, q, ge); ew_store<3, FULL>(d_light, q, gf);
     }
 };
 struct PsnFwd {
     TIn pos, view, pn, sn, st, gn; int two_sided, opengl; float *out;
-    __device__ void run(const Grid &g, const Px4 &q) const
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
     {
         float a[4][3], b[4][3], c[4][3], d[4][3], e[4][3], f[4][3], o[4][3];
-        ew_load<3>(pos, g, q, a); ew_load<3>(view, g, q, b); ew_load<3>(pn, g, q, c);
-        ew_load<3>(sn, g, q, d); ew_load<3>(st, g, q, e); ew_load<3>(gn, g, q, f);
+        ew_load<3, FULL>(pos, g, q, a); ew_load<3, FULL>(view, g, q, b); ew_load<3, FULL>(pn, g, q, c);
+        ew_load<3, FULL>(sn, g, q, d); ew_load<3, FULL>(st, g, q, e); ew_load<3, FULL>(gn, g, q, f);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             f3 smooth_nrm = safe_normalize(to3(d[k])), smooth_tng = safe_normalize(to3(e[k]));
@@ -313,17 +319,17 @@ struct PsnFwd {
             f3 res = (two_sided && dot(view_vec, geom) < 0.0f) ? fwd_bend_normal(view_vec, -sh, -geom) : fwd_bend_normal(view_vec, sh, geom);
             from3(o[k], res);
         }
-        ew_store<3>(out, q, o);
+        ew_store<3, FULL>(out, q, o);
     }
 };
 struct PsnBwd {
     TIn pos, view, pn, sn, st, gn, dout; int two_sided, opengl;
     float *d_pos, *d_view, *d_pn, *d_sn, *d_st, *d_gn;
-    __device__ void run(const Grid &g, const Px4 &q) const
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
     {
         float a[4][3], b[4][3], c[4][3], d[4][3], e[4][3], f[4][3], go[4][3];
-        ew_load<3>(pos, g, q, a); ew_load<3>(view, g, q, b); ew_load<3>(pn, g, q, c);
-        ew_load<3>(sn, g, q, d); ew_load<3>(st, g, q, e); ew_load<3>(gn, g, q, f); ew_load<3>(dout, g, q, go);
+        ew_load<3, FULL>(pos, g, q, a); ew_load<3, FULL>(view, g, q, b); ew_load<3, FULL>(pn, g, q, c);
+        ew_load<3, FULL>(sn, g, q, d); ew_load<3, FULL>(st, g, q, e); ew_load<3, FULL>(gn, g, q, f); ew_load<3, FULL>(dout, g, q, go);
         float ga[4][3], gb[4][3], gc[4][3], gd[4][3], ge[4][3], gf[4][3];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -346,8 +352,8 @@ struct PsnBwd {
             bwd_safe_normalize(_st, d__st, dst);
             from3(ga[k], -d__vv); from3(gb[k], d__vv); from3(gc[k], dp); from3(gd[k], d__sn); from3(ge[k], d__st); from3(gf[k], d_geom);
         }
-        ew_store<3>(d_pos, q, ga); ew_store<3>(d_view, q, gb); ew_store<3>(d_pn, q, gc);
-        ew_store<3>(d_sn, q, gd); ew_store<3>(d_st, q, ge); ew_store<3>(d_gn, q, gf);
+        ew_store<3, FULL>(d_pos, q, ga); ew_store<3, FULL>(d_view, q, gb); ew_store<3, FULL>(d_pn, q, gc);
+        ew_store<3, FULL>(d_sn, q, gd); ew_store<3, FULL>(d_st, q, ge); ew_store<3, FULL>(d_gn, q, gf);
     }
 };
 
