@@ -163,6 +163,22 @@ int mcs_prepare_shading_normal_bwd(const mcs_tensor *pos, const mcs_tensor *view
                                    float *d_pos, float *d_view_pos, float *d_perturbed_nrm, float *d_smooth_nrm, float *d_smooth_tng, float *d_geom_nrm,
                                    mcs_stream s);
 
+/* ---- image loss: replaces image_loss_fwd / image_loss_bwd, renderutils/c_src/torch_bindings.cpp:739-800
+ *      (loss.cu:105-227).  loss: 0 l1, 1 mse, 2 relmse, 3 smape, 4 n2n (FIX: the reference's strToLoss maps "n2n" to l1);
+ *      tonemapper: 0 none, 1 log_srgb.  Forward writes mcs_image_loss_num_partials(N,H,W) deterministic per-CTA partial sums of
+ *      mean_c(loss) -- the caller sums them and divides by N*H*W exactly like renderutils/ops.py:494.  Backward takes the upstream
+ *      gradient of those partials ([P,1,1,1] view, or one broadcast value) and writes contiguous [N,H,W,3] gradients. */
+int mcs_image_loss_num_partials(int32_t N, int32_t H, int32_t W);
+int mcs_image_loss_fwd(const mcs_tensor *img, const mcs_tensor *target, int32_t loss, int32_t tonemapper, float *partials, mcs_stream s);
+int mcs_image_loss_bwd(const mcs_tensor *img, const mcs_tensor *target, int32_t loss, int32_t tonemapper, const mcs_tensor *d_partials,
+                       float *d_img, float *d_target, mcs_stream s);
+
+/* ---- batched 4x4 transform (row f3): replaces xfm_fwd / xfm_bwd, renderutils/c_src/torch_bindings.cpp:803-864 (mesh.cu:19-90).
+ *      points as a (1|B, V, 3, 1) view, matrix as (B, 4, 4, 1); out contiguous [B,V,4] (is_points) or [B,V,3] (vectors);
+ *      d_out (B, V, 4|3, 1) view; d_points contiguous [B,V,3] (a broadcast input's gradient is reduced by the caller). */
+int mcs_xfm_fwd(const mcs_tensor *points, const mcs_tensor *matrix, int32_t is_points, float *out, mcs_stream s);
+int mcs_xfm_bwd(const mcs_tensor *points, const mcs_tensor *matrix, const mcs_tensor *d_out, int32_t is_points, float *d_points, mcs_stream s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 _LIBDIR = os.path.join(_PKG, "lib")
 LIB_PATH = os.environ.get("MCS_LIB", os.path.join(_LIBDIR, "libmcshade.so"))     # MCS_LIB: developer override (kernel variants)
-SOURCES = ["core.cu", "elementwise.cu", "denoise.cu", "bvh.cu", "envshade.cu"]
+SOURCES = ["core.cu", "elementwise.cu", "denoise.cu", "bvh.cu", "envshade.cu", "lossmesh.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 
 
@@ -102,6 +102,11 @@ _SIGS = {
     "mcs_pbr_bsdf_bwd": ([_T] * 6 + [C.c_float, C.c_int32, _T] + [_P] * 7, C.c_int),
     "mcs_prepare_shading_normal_fwd": ([_T] * 6 + [C.c_int32, C.c_int32, _P, _P], C.c_int),
     "mcs_prepare_shading_normal_bwd": ([_T] * 6 + [C.c_int32, C.c_int32, _T] + [_P] * 7, C.c_int),
+    "mcs_image_loss_num_partials": ([C.c_int32] * 3, C.c_int),
+    "mcs_image_loss_fwd": ([_T, _T, C.c_int32, C.c_int32, _P, _P], C.c_int),
+    "mcs_image_loss_bwd": ([_T, _T, C.c_int32, C.c_int32, _T, _P, _P, _P], C.c_int),
+    "mcs_xfm_fwd": ([_T, _T, C.c_int32, _P, _P], C.c_int),
+    "mcs_xfm_bwd": ([_T, _T, _T, C.c_int32, _P, _P], C.c_int),
 }
 EXPORTED_SYMBOLS = sorted(_SIGS)
 

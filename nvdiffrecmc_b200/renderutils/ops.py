@@ -233,3 +233,96 @@ def pbr_bsdf(kd, arm, pos, nrm, view_pos, light_pos, min_roughness=0.08, bsdf="l
     else:
         out = _pbr_bsdf_func.apply(kd, arm, pos, nrm, view_pos, light_pos, min_roughness, BSDF)
     return _finite(out, "pbr_bsdf")
+
+
+# ---------------------------------------------------------------------------------------------
+# Row f3 of SURVEY section 8: image loss and mesh transforms
+_LOSS_IDS = {"l1": 0, "mse": 1, "relmse": 2, "smape": 3, "n2n": 4}
+
+
+class _image_loss_func(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, target, loss, tonemapper):
+        img, target = _prep(img, target)
+        ctx.loss, ctx.tonemapper = loss, tonemapper
+        ctx.save_for_backward(img, target)
+        N, H, W = _grid(img, target)
+        nparts = L.lib().mcs_image_loss_num_partials(N, H, W)
+        out = torch.empty(nparts, dtype=torch.float32, device=img.device)
+        a, b = L.nhwc(img), L.nhwc(target)
+        L.check(L.lib().mcs_image_loss_fwd(C.byref(a), C.byref(b), _LOSS_IDS.get(loss, 0), 1 if tonemapper == "log_srgb" else 0, out.data_ptr(),
+                                           L.stream_ptr()), "image_loss (forward)")
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        img, target = ctx.saved_tensors
+        N, H, W = _grid(img, target)
+        gi = torch.empty(N, H, W, 3, dtype=torch.float32, device=img.device)
+        gt = torch.empty(N, H, W, 3, dtype=torch.float32, device=img.device)
+        d = dout.float()
+        dd = L._desc(d.data_ptr(), [d.shape[0], 1, 1, 1], [d.stride(0), 0, 0, 0])
+        a, b = L.nhwc(img), L.nhwc(target)
+        L.check(L.lib().mcs_image_loss_bwd(C.byref(a), C.byref(b), _LOSS_IDS.get(ctx.loss, 0), 1 if ctx.tonemapper == "log_srgb" else 0, C.byref(dd),
+                                           gi.data_ptr(), gt.data_ptr(), L.stream_ptr()), "image_loss (backward)")
+        return _reduce_like(gi, img), _reduce_like(gt, target), None, None
+
+
+def image_loss(img, target, loss='l1', tonemapper='none', use_python=False):
+    """renderutils/ops.py:476-498.  HDR image loss, tonemapping + loss fused in one kernel.  loss in ['l1', 'mse', 'smape', 'relmse', 'n2n']
+    (FIX: the reference's CUDA path silently computes l1 for 'n2n'), tonemapper in ['none', 'log_srgb'].  Returns a scalar."""
+    if use_python:
+        from .loss import image_loss_fn
+        out = image_loss_fn(img, target, loss, tonemapper)
+    else:
+        out = _image_loss_func.apply(img, target, loss, tonemapper)
+        out = torch.sum(out) / (img.shape[0] * img.shape[1] * img.shape[2])
+    return _finite(out, "image_loss")
+
+
+class _xfm_func(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, matrix, isPoints):
+        L.require_cuda(points, matrix)
+        points = points if points.dtype == torch.float32 else points.float()
+        matrix = matrix if matrix.dtype == torch.float32 else matrix.float()
+        if points.dim() != 3 or points.shape[2] != 3 or matrix.dim() != 3:
+            raise RuntimeError("xfm: points must be [1|B, V, 3] and matrix [B, 4, 4]")
+        ctx.save_for_backward(points, matrix)
+        ctx.isPoints = isPoints
+        B, V = matrix.shape[0], points.shape[1]
+        out = torch.empty(B, V, 4 if isPoints else 3, dtype=torch.float32, device=points.device)
+        p = L._desc(points.data_ptr(), list(points.shape) + [1], list(points.stride()) + [0])
+        m = L._desc(matrix.data_ptr(), list(matrix.shape) + [1], list(matrix.stride()) + [0])
+        L.check(L.lib().mcs_xfm_fwd(C.byref(p), C.byref(m), int(isPoints), out.data_ptr(), L.stream_ptr()), "xfm (forward)")
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        points, matrix = ctx.saved_tensors
+        B, V = matrix.shape[0], points.shape[1]
+        d = dout.float()
+        g = torch.empty(B, V, 3, dtype=torch.float32, device=points.device)
+        p = L._desc(points.data_ptr(), list(points.shape) + [1], list(points.stride()) + [0])
+        m = L._desc(matrix.data_ptr(), list(matrix.shape) + [1], list(matrix.stride()) + [0])
+        dd = L._desc(d.data_ptr(), list(d.shape) + [1], list(d.stride()) + [0])
+        L.check(L.lib().mcs_xfm_bwd(C.byref(p), C.byref(m), C.byref(dd), int(ctx.isPoints), g.data_ptr(), L.stream_ptr()), "xfm (backward)")
+        return (g.sum_to_size(points.shape) if tuple(g.shape) != tuple(points.shape) else g), None, None
+
+
+def xfm_points(points, matrix, use_python=False):
+    """renderutils/ops.py:501-519: [1|B,V,3] x [B,4,4] -> homogeneous [B,V,4]."""
+    if use_python:
+        out = torch.matmul(torch.nn.functional.pad(points, pad=(0, 1), mode='constant', value=1.0), torch.transpose(matrix, 1, 2))
+    else:
+        out = _xfm_func.apply(points, matrix, True)
+    return _finite(out, "xfm_points")
+
+
+def xfm_vectors(vectors, matrix, use_python=False):
+    """renderutils/ops.py:521-540: [1|B,V,3] x [B,4,4] -> [B,V,3] (w = 0)."""
+    if use_python:
+        out = torch.matmul(torch.nn.functional.pad(vectors, pad=(0, 1), mode='constant', value=0.0), torch.transpose(matrix, 1, 2))[..., 0:3].contiguous()
+    else:
+        out = _xfm_func.apply(vectors, matrix, False)
+    return _finite(out, "xfm_vectors")

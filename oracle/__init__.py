@@ -324,6 +324,41 @@ class Oracle:
         o = self.bilateral_fwd(col, nrm, zdz, sigma)
         return o[..., 0:3] / o[..., 3:4]
 
+    # ------------------------------------------------------------------ row f3: image loss, xfm
+    _LOSSES = {"l1": 0, "mse": 1, "relmse": 2, "smape": 3, "n2n": 4}
+
+    def image_loss(self, img, target, loss="l1", tonemapper="none"):
+        """renderutils/ops.py:476-498: mean over pixels of mean_c(loss)."""
+        lead, (a, b) = self._bc(img, target, chans=[3, 3])
+        n = int(np.prod(lead)); px = np.zeros(n, self.dt)
+        self.lib.orc_image_loss_fwd(C.c_int(n), C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data), C.c_int(self._LOSSES[loss]),
+                                    C.c_int(1 if tonemapper == "log_srgb" else 0), C.c_void_p(px.ctypes.data))
+        return px.sum(dtype=np.float64) / n
+
+    def image_loss_bwd(self, img, target, loss="l1", tonemapper="none", dout=1.0):
+        lead, (a, b) = self._bc(img, target, chans=[3, 3])
+        n = int(np.prod(lead)); dpx = np.full(n, dout / n, self.dt)
+        gi = np.zeros(lead + (3,), self.dt); gt = np.zeros(lead + (3,), self.dt)
+        self.lib.orc_image_loss_bwd(C.c_int(n), C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data), C.c_int(self._LOSSES[loss]),
+                                    C.c_int(1 if tonemapper == "log_srgb" else 0), C.c_void_p(dpx.ctypes.data), C.c_void_p(gi.ctypes.data),
+                                    C.c_void_p(gt.ctypes.data))
+        return gi, gt
+
+    def xfm(self, points, matrix, is_points=True):
+        pts = self._a(points); m = self._a(matrix)
+        B, V = m.shape[0], pts.shape[1]
+        out = np.zeros((B, V, 4 if is_points else 3), self.dt)
+        self.lib.orc_xfm_fwd(C.c_int(B), C.c_int(pts.shape[0]), C.c_int(V), C.c_void_p(pts.ctypes.data), C.c_void_p(m.ctypes.data), C.c_int(int(is_points)),
+                             C.c_void_p(out.ctypes.data))
+        return out
+
+    def xfm_bwd(self, matrix, dout, is_points=True):
+        m = self._a(matrix); g = self._a(dout)
+        B, V = g.shape[0], g.shape[1]
+        out = np.zeros((B, V, 3), self.dt)
+        self.lib.orc_xfm_bwd(C.c_int(B), C.c_int(V), C.c_void_p(m.ctypes.data), C.c_void_p(g.ctypes.data), C.c_int(int(is_points)), C.c_void_p(out.ctypes.data))
+        return out
+
     # ------------------------------------------------------------------ det math (fp32 only)
     def det_sincos(self, a):
         a = np.ascontiguousarray(a, np.float32); s = np.zeros_like(a); c = np.zeros_like(a)

@@ -86,3 +86,28 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_loss_xfm():
+    """Row f3: ru.image_loss / ru.xfm_points / ru.xfm_vectors with use_python=True (render/renderutils/loss.py, ops.py:515,535)."""
+    g = torch.Generator().manual_seed(5)
+    out = {}
+    img = (torch.rand(2, 9, 7, 3, generator=g) * 4).requires_grad_(True); tgt = (torch.rand(2, 9, 7, 3, generator=g) * 4).requires_grad_(True)
+    out['img'] = img.detach().numpy(); out['tgt'] = tgt.detach().numpy()
+    for loss in ['l1', 'mse', 'smape', 'relmse']:
+        for tm in ['none', 'log_srgb']:
+            img.grad = None; tgt.grad = None
+            v = ru.image_loss(img, tgt, loss=loss, tonemapper=tm, use_python=True); v.backward()
+            out['%s_%s' % (loss, tm)] = np.float64(v.item()); out['%s_%s_gi' % (loss, tm)] = img.grad.numpy().copy(); out['%s_%s_gt' % (loss, tm)] = tgt.grad.numpy().copy()
+    pts = torch.rand(1, 11, 3, generator=g).requires_grad_(True); mtx = torch.rand(3, 4, 4, generator=g)
+    o = ru.xfm_points(pts, mtx, use_python=True); d = torch.rand(o.shape, generator=g); o.backward(d)
+    out.update(pts=pts.detach().numpy(), mtx=mtx.numpy(), xfmp=o.detach().numpy(), xfmp_d=d.numpy(), xfmp_g=pts.grad.numpy().copy())
+    pts.grad = None
+    o = ru.xfm_vectors(pts, mtx, use_python=True); d = torch.rand(o.shape, generator=g); o.backward(d)
+    out.update(xfmv=o.detach().numpy(), xfmv_d=d.numpy(), xfmv_g=pts.grad.numpy().copy())
+    np.savez_compressed(os.path.join(OUT, 'ref_loss_xfm.npz'), **out)
+    print("wrote ref_loss_xfm")
+
+
+if __name__ == "__main__":
+    make_loss_xfm()
