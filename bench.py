@@ -3,7 +3,7 @@
 
 One "step" = one training iteration's worth of the hot path on one batch of synthetic views:
     update_pdf -> LBVH rebuild -> prepare_shading_normal -> env_shade fwd (2*N^2 shadow rays / covered pixel)
-    -> fused bilateral denoise (diffuse + specular) -> recombine + MSE loss -> full backward
+    -> fused bilateral denoise (diffuse + specular) -> recombine + fused log-sRGB L1 image loss -> full backward
     (denoise bwd, env_shade bwd re-tracing all rays, shading-normal bwd, texture scatter)
     -> [N > 1: one NCCL all-reduce over the flat parameter-gradient bucket].
 value = shadow rays processed per second over the whole job (fwd + bwd rays, all ranks), in Mrays/s;
@@ -177,7 +177,7 @@ class GpuWorkload:
         guide = torch.cat((nrm, zdz), dim=-1)
         diff, spec = self.denoiser.forward2(torch.cat((diff, guide), dim=-1), torch.cat((spec, guide), dim=-1))   # render.py:120-121
         shaded = diff * kd * (1.0 - ks[..., 2:3]) + spec                             # render.py:126-127
-        loss = torch.nn.functional.mse_loss(shaded, self.target)
+        loss = ru.image_loss(shaded, self.target, loss='l1', tonemapper='log_srgb')        # train.py:57-58 ('logl1', the default loss)
         if timers is not None:
             timers["bwd0"].record()
         loss.backward()

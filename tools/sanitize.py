@@ -1,0 +1,29 @@
+"""Developer tool: tiny end-to-end pass of every kernel family, meant to run under compute-sanitizer
+(memcheck / racecheck / initcheck) -- SURVEY.md section 5 "race detection"."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+from common import make_case
+import nvdiffrecmc_b200.optixutils as ou
+import nvdiffrecmc_b200.renderutils as ru
+
+dev = torch.device("cuda:0")
+for N in (4, 9):
+    c = make_case(res=12, B=2, N=N, perm_rows=64)
+    t = lambda k: torch.tensor(c[k], device=dev)
+    ctx = ou.OptiXContext()
+    ou.optix_build_bvh(ctx, t("verts"), t("tris"), 1)
+    pos, kd, ks, light = [t(k).requires_grad_(True) for k in ("pos", "kd", "ks", "light")]
+    nrm = ru.prepare_shading_normal(pos, t("view"), None, t("smooth_nrm"), t("tangent"), t("geom_nrm"))
+    d, s = ou.optix_env_shade(ctx, t("mask"), t("ro"), pos, nrm, t("view"), kd, ks, light, t("pdf"), t("rows"), t("cols"), n_samples_x=N, rnd_seed=3,
+                              perms=t("perms"))
+    zdz = torch.stack([t("depth"), torch.full_like(t("depth"), 0.01)], -1)
+    a, b = ou.bilateral_denoiser2(d, s, torch.nn.functional.normalize(nrm.detach() + 1e-6, dim=-1), zdz, 1.0)
+    loss = ru.image_loss(a * kd + b, torch.rand_like(a), loss="l1", tonemapper="log_srgb")
+    loss.backward()
+    ou.optix_build_bvh(ctx, t("verts"), t("tris"), 0)
+    v = ou.trace_visibility(ctx, t("ro").reshape(-1, 3), torch.nn.functional.normalize(torch.randn(c["ro"].size // 3, 3, device=dev), dim=-1))
+    pts = ru.xfm_points(t("verts")[None], torch.rand(2, 4, 4, device=dev))
+torch.cuda.synchronize()
+print("sanitize workload ok", float(loss), int(v.sum()), tuple(pts.shape))
