@@ -434,13 +434,15 @@ def main():
     hbm, hbm_src = peaks()
     N = wl["n_samples_x"]
     tc = traversal_counts(wl)
+    tfrac, vfrac = traced_fraction(w)
+    vfrac_pre = vfrac
     # SURVEY 8d:  A_ray = P/(2N^2) + 4 [perms] + 16 [light texel + pdf] + 44 [CDF probes] + 32*nodes + 36*tris   (+12 B/ray light-grad atomics in bwd)
     a_fwd = 88.0 / (2 * N * N) + 4 + 16 + 44 + 32 * tc["nodes_per_ray"] + 36 * tc["tris_per_ray"]
-    # backward replays the forward hit record: no traversal bytes, + 1 bit/ray of record
-    a_bwd = 136.0 / (2 * N * N) + 4 + 16 + 44 + 12 + 0.125
+    # backward replays the forward RAY RECORD: per covered pixel 136 B (G-buffer + upstream + gradients), per EVALUATED ray
+    # 20 B record + 12 B env texel + 12 B gradient atomics; nothing for sampling or traversal.  Expressed per logical ray:
+    a_bwd = 136.0 / (2 * N * N) + vfrac_pre * (20 + 12 + 12)
     ach_fwd = a_fwd * w.rays_per_pass / (k_fwd_ms * 1e-3) / 1e9
     ach_bwd = a_bwd * w.rays_per_pass / (k_bwd_ms * 1e-3) / 1e9
-    tfrac, vfrac = traced_fraction(w)
     roof = {"bound": "hbm", "kernel": "env_shade_kernel<0> (fused env sampling + shadow rays + BSDF, forward)",
             "achieved": round(ach_fwd, 2), "peak": hbm, "unit": "GB/s", "frac": round(ach_fwd / hbm, 4), "traffic": None,
             "peak_source": hbm_src, "algorithmic_bytes_per_ray": round(a_fwd, 1), "rays_per_launch": w.rays_per_pass,
@@ -448,7 +450,7 @@ def main():
             "canonical_traversal": tc,
             "traced_fraction": round(tfrac, 4), "visible_fraction": round(vfrac, 4),
             "frac_traced_rays_only": round(ach_fwd * tfrac / hbm, 4),
-            "backward": {"kernel": "env_shade_kernel<1> (hit-record replay: sampling + adjoint BSDF + gradient scatter, no traversal)", "achieved": round(ach_bwd, 2), "frac": round(ach_bwd / hbm, 4), "kernel_ms": round(k_bwd_ms, 3),
+            "backward": {"kernel": "env_shade_replay_kernel (ray-record replay: adjoint BSDF + gradient scatter only; no sampling, no traversal)", "achieved": round(ach_bwd, 2), "frac": round(ach_bwd / hbm, 4), "kernel_ms": round(k_bwd_ms, 3),
                          "algorithmic_bytes_per_ray": round(a_bwd, 1), "mrays_per_s": round(w.rays_per_pass / k_bwd_ms / 1e3, 1)},
             "note": "achieved = LOGICAL bytes (SURVEY 8d model: every CDF probe, texel, canonical-LBVH node and triangle counted as a memory access) "
                     "x logical rays / kernel time; all tables of this mesh are L1/L2 resident so the physical DRAM traffic (`traffic`) is ~%.1f B/ray "
@@ -489,7 +491,8 @@ def main():
                    "coverage_rank0": round(w.covered / (wl["views_per_gpu"] * wl["res"] ** 2), 4),
                    "parallelism": "dp%d over views, one NCCL all-reduce of the flat gradient bucket (%.1f MB)" % (world, w.flat_grad.numel() * 4 / 1e6),
                    "l2_policy": "per-step inputs (G-buffer %.0f MB + intermediates) exceed the 126 MB L2" % (w.bytes_h2d / 1e6)},
-        "rays_counted": "covered px x 2N^2 per pass x 2 passes: the reference traces forward AND backward; here forward traces, backward replays the 1-bit/sample hit record",
+        "rays_counted": "covered px x 2N^2 per pass x 2 passes: the reference traces forward AND backward; here forward traces and records the evaluated rays (20 B/sample slot), backward replays the record",
+        "ray_record_bytes": int(wl["views_per_gpu"] * wl["res"] ** 2 * (2 * N * N * 20 + 4)),
         "train_iters_per_s": round(1e3 / ms_step, 3),
         "breakdown_ms": {"env_shade_fwd": round(fwd_ms, 3), "backward_all": round(bwd_all_ms, 3), "env_shade_fwd_kernel": round(k_fwd_ms, 3),
                          "env_shade_bwd_kernel": round(k_bwd_ms, 3)},

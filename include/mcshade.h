@@ -75,14 +75,18 @@ int mcs_trace_closest(mcs_ctx *ctx, const float *ro, const float *rd, int64_t n,
  *      hit_record (optional, may be NULL): uint32 [B,H,W,ceil(2*n_samples_x^2/32)], receives one bit per sample slot
  *      w (w < N^2: light sample of stratum w; else BSDF sample of stratum w-N^2): 1 = shadow ray occluded.  Passing the
  *      same buffer to mcs_env_shade_bwd (same seed, same inputs) lets the backward pass REPLAY visibility instead of
- *      re-tracing every ray as the reference does (torch_bindings.cpp:266-267 launches the same program with backward=1). */
+ *      re-tracing every ray as the reference does (torch_bindings.cpp:266-267 launches the same program with backward=1).
+ *      rec_count / rec_rays (optional, together): the full RAY RECORD -- rec_count uint32 [B,H,W] = number of rays that were
+ *      evaluated for the pixel (visible, or occluded with shadow_scale < 1), rec_rays fp32 [B,H,W,5,rec_slots] =
+ *      (dx, dy, dz, MIS weight, env texel | occluded << 31) in evaluation order, rec_slots >= 2*n_samples_x^2.  With it the
+ *      backward pass needs neither sampling nor traversal: see mcs_env_shade_bwd_replay. */
 int mcs_env_shade_fwd(mcs_ctx *ctx,
                       const mcs_tensor *mask, const mcs_tensor *ro, const mcs_tensor *gb_pos, const mcs_tensor *gb_normal,
                       const mcs_tensor *gb_view_pos, const mcs_tensor *gb_kd, const mcs_tensor *gb_ks,
                       const mcs_tensor *light, const mcs_tensor *pdf, const mcs_tensor *rows, const mcs_tensor *cols,
                       const mcs_tensor *perms,
                       uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
-                      float *diff, float *spec, uint32_t *hit_record, mcs_stream stream);
+                      float *diff, float *spec, uint32_t *hit_record, uint32_t *rec_count, float *rec_rays, int32_t rec_slots, mcs_stream stream);
 
 /* Gradient outputs: gb_pos_grad, gb_normal_grad, gb_kd_grad, gb_ks_grad contiguous [B,H,W,3]
  * (fully written), light_grad contiguous [Hl,Wl,3] (zeroed by the call, then accumulated). */
@@ -95,6 +99,13 @@ int mcs_env_shade_bwd(mcs_ctx *ctx,
                       const mcs_tensor *diff_grad, const mcs_tensor *spec_grad,
                       float *gb_pos_grad, float *gb_normal_grad, float *gb_kd_grad, float *gb_ks_grad, float *light_grad,
                       const uint32_t *hit_record /* NULL = re-trace */, mcs_stream stream);
+
+/* Backward from the ray record written by mcs_env_shade_fwd (same G-buffer, light and shadow_scale): one warp per pixel walks
+ * the recorded rays and runs only the adjoint BSDF + env-map gradient scatter.  Outputs as mcs_env_shade_bwd. */
+int mcs_env_shade_bwd_replay(const mcs_tensor *gb_pos, const mcs_tensor *gb_normal, const mcs_tensor *gb_view_pos, const mcs_tensor *gb_kd,
+                             const mcs_tensor *gb_ks, const mcs_tensor *light, uint32_t bsdf, uint32_t n_samples_x, float shadow_scale,
+                             const mcs_tensor *diff_grad, const mcs_tensor *spec_grad, const uint32_t *rec_count, const float *rec_rays, int32_t rec_slots,
+                             float *gb_pos_grad, float *gb_normal_grad, float *gb_kd_grad, float *gb_ks_grad, float *light_grad, mcs_stream stream);
 
 /* Debug/parity hook: forward pass that also records, per pixel and per ray slot
  * (slot = 2*i for the light sample of stratum i, 2*i+1 for the BSDF sample), the env texel read

@@ -62,6 +62,9 @@ struct EnvParams {
     uint32_t *hit_out;              // optional: per-pixel visibility record written by the forward pass
     const uint32_t *hit_in;         // optional: record replayed by the backward pass instead of tracing
     int hit_words;                  // uint32 words per pixel = ceil(2 N^2 / 32)
+    uint32_t *rec_count;            // optional ray record written by the forward pass: evaluated rays per pixel ...
+    float *rec_rays;                // ... and their (dx, dy, dz, mis, tex|occluded<<31) as [pixel][5][rec_slots] words
+    int rec_slots;
     // bwd
     TView diff_grad, spec_grad;
     float *pos_grad, *nrm_grad, *kd_grad, *ks_grad, *light_grad;
@@ -603,6 +606,7 @@ __global__ void __launch_bounds__(NW * 32, 1) env_shade_kernel(const EnvParams p
                             float *d = p.diff + mypix * 3, *s = p.spec + mypix * 3;
                             d[0] = d[1] = d[2] = 0.0f; s[0] = s[1] = s[2] = 0.0f;
                             if (p.hit_out) for (int k = 0; k < p.hit_words; ++k) p.hit_out[(size_t)mypix * p.hit_words + k] = 0u;
+                            if (p.rec_count) p.rec_count[mypix] = 0u;
                         } else {
                             float *a = p.pos_grad + mypix * 3, *b = p.nrm_grad + mypix * 3, *c = p.kd_grad + mypix * 3, *d = p.ks_grad + mypix * 3;
                             a[0] = a[1] = a[2] = 0.0f; b[0] = b[1] = b[2] = 0.0f; c[0] = c[1] = c[2] = 0.0f; d[0] = d[1] = d[2] = 0.0f;
@@ -627,6 +631,7 @@ __global__ void __launch_bounds__(NW * 32, 1) env_shade_kernel(const EnvParams p
         // accumulators live across queue fills when one pixel needs several (items > SEG)
         f3 accD = F3(0.0f), accS = F3(0.0f);
         f3 g_kd = F3(0.0f), g_ks = F3(0.0f), g_nrm = F3(0.0f), g_wo = F3(0.0f);
+        int rec_off = 0;
 
         for (int sub = 0; sub < nsub; ++sub) {
             const int w0 = sub * SEG, w1 = min(items, w0 + SEG);
@@ -690,6 +695,18 @@ __global__ void __launch_bounds__(NW * 32, 1) env_shade_kernel(const EnvParams p
                     vn += __popc(m);
                 }
                 __syncwarp();
+                if (MODE != 1 && p.rec_count != nullptr) {
+                    // ray record for the backward pass: exactly the rays evaluated below, in evaluation order (coalesced SoA rows)
+                    float *rr = p.rec_rays + (size_t)mypx * 5 * p.rec_slots;
+                    for (int k = lane; k < vn; k += 32) {
+                        const int e = q.vlist[qb + k];
+                        const int o = rec_off + k;
+                        rr[o] = q.dx[e]; rr[p.rec_slots + o] = q.dy[e]; rr[2 * p.rec_slots + o] = q.dz[e]; rr[3 * p.rec_slots + o] = q.mis[e];
+                        rr[4 * p.rec_slots + o] = __uint_as_float(q.tex[e]);
+                    }
+                    rec_off += vn;
+                    if (sub == nsub - 1 && lane == 0) p.rec_count[mypx] = (uint32_t)rec_off;
+                }
                 const PixelIn px = load_pixel(p, mypx);
                 const f3 wo_f = F3(q.wo[warp][0], q.wo[warp][1], q.wo[warp][2]);
                 f3 dgrad = F3(0.0f), sgrad = F3(0.0f);
@@ -756,6 +773,84 @@ __global__ void __launch_bounds__(NW * 32, 1) env_shade_kernel(const EnvParams p
                 }
             }
             __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward from the forward pass's RAY RECORD: no sampling, no traversal -- per pixel the warp walks the recorded rays
+// (direction, MIS weight, env texel, occluded flag) in the order the forward pass evaluated them and runs the adjoint BSDF
+// + env-map gradient scatter (process_sample's backward branch, kernel.cu:422-457).  One warp per pixel, plain grid.
+// ---------------------------------------------------------------------------------------------
+struct ReplayParams {
+    TView pos, nrm, view, kd, ks, diff_grad, spec_grad;
+    const float *light; int l_s1, l_s2, l_s3; int Hl, Wl;
+    const uint32_t *rec_count; const float *rec_rays; int rec_slots;
+    int B, H, W;
+    uint32_t bsdf; float shadow_scale, sample_frac;
+    float *pos_grad, *nrm_grad, *kd_grad, *ks_grad, *light_grad;
+};
+
+__global__ void __launch_bounds__(256) env_shade_replay_kernel(const ReplayParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t npix = (int64_t)p.B * p.H * p.W;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool diffuse_only = (p.bsdf == 1u || p.bsdf == 2u);
+    const float v_occluded = 1.0f - p.shadow_scale;
+    for (int64_t chunk = warp_global; chunk * 32 < npix; chunk += nwarps) {
+        const int64_t mypix = chunk * 32 + lane;
+        const uint32_t mycnt = mypix < npix ? __ldg(p.rec_count + mypix) : 0u;
+        unsigned rem = __ballot_sync(0xFFFFFFFFu, mycnt != 0u);
+        if (mypix < npix && mycnt == 0u) {
+            float *a = p.pos_grad + mypix * 3, *b = p.nrm_grad + mypix * 3, *c = p.kd_grad + mypix * 3, *d = p.ks_grad + mypix * 3;
+            a[0] = a[1] = a[2] = 0.0f; b[0] = b[1] = b[2] = 0.0f; c[0] = c[1] = c[2] = 0.0f; d[0] = d[1] = d[2] = 0.0f;
+        }
+        while (rem) {
+            const int src = __ffs(rem) - 1;
+            rem &= rem - 1;
+            const int64_t pix = chunk * 32 + src;
+            const int cnt = (int)__shfl_sync(0xFFFFFFFFu, mycnt, src);
+            const int ix = (int)(pix % p.W); const int64_t tt = pix / p.W; const int iy = (int)(tt % p.H), iz = (int)(tt / p.H);
+            const f3 pos = p.pos.ld3(iz, iy, ix), nrm = p.nrm.ld3(iz, iy, ix), view = p.view.ld3(iz, iy, ix), kd = p.kd.ld3(iz, iy, ix), ks = p.ks.ld3(iz, iy, ix);
+            const f3 dgrad = p.diff_grad.ld3(iz, iy, ix), sgrad = p.spec_grad.ld3(iz, iy, ix);
+            const f3 wo_f = safe_normalize(view - pos);
+            const float *rr = p.rec_rays + (size_t)pix * 5 * p.rec_slots;
+            f3 g_kd = F3(0.0f), g_ks = F3(0.0f), g_nrm = F3(0.0f), g_wo = F3(0.0f);
+            for (int k = lane; k < cnt; k += 32) {
+                const f3 wi = F3(__ldg(rr + k), __ldg(rr + p.rec_slots + k), __ldg(rr + 2 * p.rec_slots + k));
+                const float mis = __ldg(rr + 3 * p.rec_slots + k);
+                const uint32_t tex = __float_as_uint(__ldg(rr + 4 * p.rec_slots + k));
+                const int tx = tex & 0xFFFFu, ty = (tex >> 16) & 0x7FFFu;
+                const float wgt = ((tex >> 31) ? v_occluded : 1.0f) * mis * p.sample_frac;
+                const float *lp = p.light + (size_t)ty * p.l_s1 + (size_t)tx * p.l_s2;
+                const f3 light_col = F3(__ldg(lp), __ldg(lp + p.l_s3), __ldg(lp + 2 * p.l_s3));
+                float diffv = 0.0f; f3 specv = F3(0.0f);
+                if (diffuse_only) diffv = fwd_lambert(nrm, wi);
+                else ox_fwd_pbr_bsdf(kd, ks, wo_f, nrm, wi, MIN_ROUGHNESS, diffv, specv);
+                const f3 lg = (dgrad * diffv + sgrad * specv) * wgt;
+                float *gp = p.light_grad + ((size_t)ty * p.Wl + tx) * 3;
+                if (lg.x != 0.0f) atomicAdd(gp, lg.x);
+                if (lg.y != 0.0f) atomicAdd(gp + 1, lg.y);
+                if (lg.z != 0.0f) atomicAdd(gp + 2, lg.z);
+                const f3 dD = dgrad * light_col * wgt, dS = sgrad * light_col * wgt;
+                if (diffuse_only) { f3 wi_grad = F3(0.0f); bwd_lambert(nrm, wi, g_nrm, wi_grad, sum(dD)); }
+                else ox_bwd_pbr_bsdf(kd, ks, wo_f, nrm, wi, MIN_ROUGHNESS, g_kd, g_ks, g_wo, g_nrm, sum(dD), dS);
+            }
+            f3 t_kd = F3(warp_sum(g_kd.x), warp_sum(g_kd.y), warp_sum(g_kd.z));
+            f3 t_ks = F3(warp_sum(g_ks.x), warp_sum(g_ks.y), warp_sum(g_ks.z));
+            f3 t_nrm = F3(warp_sum(g_nrm.x), warp_sum(g_nrm.y), warp_sum(g_nrm.z));
+            f3 t_wo = F3(warp_sum(g_wo.x), warp_sum(g_wo.y), warp_sum(g_wo.z));
+            if (lane == 0) {
+                f3 d__wo = F3(0.0f);
+                bwd_safe_normalize(view - pos, d__wo, t_wo);
+                float *a = p.pos_grad + pix * 3, *b = p.nrm_grad + pix * 3, *c = p.kd_grad + pix * 3, *d = p.ks_grad + pix * 3;
+                a[0] = -d__wo.x; a[1] = -d__wo.y; a[2] = -d__wo.z;
+                b[0] = t_nrm.x; b[1] = t_nrm.y; b[2] = t_nrm.z;
+                c[0] = t_kd.x; c[1] = t_kd.y; c[2] = t_kd.z;
+                d[0] = t_ks.x; d[1] = t_ks.y; d[2] = t_ks.z;
+            }
         }
     }
 }
@@ -864,7 +959,7 @@ int mcs_env_shade_fwd(mcs_ctx *ctx,
                       const mcs_tensor *light, const mcs_tensor *pdf, const mcs_tensor *rows, const mcs_tensor *cols,
                       const mcs_tensor *perms,
                       uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
-                      float *diff, float *spec, uint32_t *hit_record, mcs_stream stream)
+                      float *diff, float *spec, uint32_t *hit_record, uint32_t *rec_count, float *rec_rays, int32_t rec_slots, mcs_stream stream)
 {
     EnvParams p{};
     cudaStream_t s = (cudaStream_t)stream;
@@ -872,6 +967,9 @@ int mcs_env_shade_fwd(mcs_ctx *ctx,
                             shadow_scale, batch_offset, s)) return e;
     MCS_REQUIRE(diff && spec, "env_shade_fwd: null output pointer");
     p.diff = diff; p.spec = spec; p.hit_out = hit_record;
+    MCS_REQUIRE((rec_count == nullptr) == (rec_rays == nullptr), "env_shade_fwd: rec_count and rec_rays go together");
+    MCS_REQUIRE(rec_count == nullptr || rec_slots >= 2 * p.S, "env_shade_fwd: rec_slots must be >= 2 * n_samples_x^2");
+    p.rec_count = rec_count; p.rec_rays = rec_rays; p.rec_slots = rec_slots;
     return launch_env<0>(p, s);
 }
 
@@ -915,6 +1013,40 @@ int mcs_env_shade_bwd(mcs_ctx *ctx,
     p.hit_in = hit_record;
     MCS_CUDA(cudaMemsetAsync(light_grad, 0, sizeof(float) * 3 * (size_t)p.Hl * p.Wl, s));
     return launch_env<1>(p, s);
+}
+
+int mcs_env_shade_bwd_replay(const mcs_tensor *gb_pos, const mcs_tensor *gb_normal, const mcs_tensor *gb_view_pos, const mcs_tensor *gb_kd,
+                             const mcs_tensor *gb_ks, const mcs_tensor *light, uint32_t bsdf, uint32_t n_samples_x, float shadow_scale,
+                             const mcs_tensor *diff_grad, const mcs_tensor *spec_grad, const uint32_t *rec_count, const float *rec_rays, int32_t rec_slots,
+                             float *gb_pos_grad, float *gb_normal_grad, float *gb_kd_grad, float *gb_ks_grad, float *light_grad, mcs_stream stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    const mcs_tensor *all[] = {gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, diff_grad, spec_grad};
+    for (const mcs_tensor *t : all) MCS_REQUIRE(view_ok(t), "env_shade_bwd_replay: null / empty tensor argument");
+    MCS_REQUIRE(rec_count && rec_rays && rec_slots > 0, "env_shade_bwd_replay: missing ray record");
+    MCS_REQUIRE(gb_pos_grad && gb_normal_grad && gb_kd_grad && gb_ks_grad && light_grad, "env_shade_bwd_replay: null output pointer");
+    MCS_REQUIRE(bsdf <= 2u && n_samples_x >= 1u, "env_shade_bwd_replay: bad bsdf / n_samples_x");
+    ReplayParams p{};
+    p.B = diff_grad->sizes[0]; p.H = diff_grad->sizes[1]; p.W = diff_grad->sizes[2];
+    p.pos = make_view(gb_pos); p.nrm = make_view(gb_normal); p.view = make_view(gb_view_pos); p.kd = make_view(gb_kd); p.ks = make_view(gb_ks);
+    p.diff_grad = make_view(diff_grad); p.spec_grad = make_view(spec_grad);
+    p.Hl = light->sizes[1]; p.Wl = light->sizes[2];
+    p.light = (const float *)light->ptr; p.l_s1 = light->strides[1]; p.l_s2 = light->strides[2]; p.l_s3 = light->strides[3];
+    p.rec_count = rec_count; p.rec_rays = rec_rays; p.rec_slots = rec_slots;
+    p.bsdf = bsdf; p.shadow_scale = shadow_scale;
+    p.sample_frac = 1.0f / (float)(n_samples_x * n_samples_x);
+    p.pos_grad = gb_pos_grad; p.nrm_grad = gb_normal_grad; p.kd_grad = gb_kd_grad; p.ks_grad = gb_ks_grad; p.light_grad = light_grad;
+    MCS_CUDA(cudaMemsetAsync(light_grad, 0, sizeof(float) * 3 * (size_t)p.Hl * p.Wl, s));
+    int dev = 0, sms = 0;
+    MCS_CUDA(cudaGetDevice(&dev));
+    MCS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t npix = (int64_t)p.B * p.H * p.W;
+    int64_t want = (npix + 255) / 256;
+    int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+    if (grid < 1) grid = 1;
+    env_shade_replay_kernel<<<grid, 256, 0, s>>>(p);
+    MCS_LAUNCH_CHECK();
+    return 0;
 }
 
 }  // extern "C"

@@ -12,7 +12,14 @@ import torch
 from .. import _lib as L
 
 _BSDF_MODES = ['pbr', 'diffuse', 'white']      # ops.py:136 -- order matters, it is the kernel's enum
-HIT_RECORD_REPLAY = True                        # backward replays the forward pass's visibility bits when the seed is shared
+# What the forward pass records for the backward pass when the seed is shared (rnd_seed is not None):
+#   "rays": the evaluated rays themselves (direction, MIS weight, env texel: 20 B per sample slot = 2.5 KB/pixel at n_samples_x = 8);
+#           backward = adjoint BSDF + gradient scatter only (no sampling, no traversal);
+#   "bits": 1 visibility bit per sample (16 B/pixel); backward re-generates the samples but skips the traversal;
+#   None  : nothing; backward re-traces like the reference (torch_bindings.cpp:266-267).
+# "rays" falls back to "bits" when the record would exceed RAY_RECORD_MAX_BYTES.
+HIT_RECORD_REPLAY = "rays"
+RAY_RECORD_MAX_BYTES = 32 << 30
 
 
 def _f32(t, name):
@@ -99,13 +106,25 @@ class _optix_env_shade_func(torch.autograd.Function):
         # rays of the forward pass, so it can replay the record instead of re-tracing (the reference re-traces, torch_bindings.cpp:266).
         # Not possible in decorrelated mode (rnd_seed=None draws a different seed for backward, ops.py:83,100).
         need_grad = any(t.requires_grad for t in (gb_pos, gb_normal, gb_kd, gb_ks, light))
-        hit = None
-        if HIT_RECORD_REPLAY and rnd_seed is not None and need_grad:
-            hit = torch.empty(B, H, W, (2 * n_samples_x * n_samples_x + 31) // 32, dtype=torch.int32, device=ro.device)
+        hit = rec_cnt = rec_rays = None
+        slots = 2 * n_samples_x * n_samples_x
+        mode = HIT_RECORD_REPLAY if (rnd_seed is not None and need_grad) else None
+        if mode is True:
+            mode = "bits"
+        if mode == "rays" and B * H * W * slots * 20 > RAY_RECORD_MAX_BYTES:
+            mode = "bits"
+        if mode == "rays":
+            rec_cnt = torch.empty(B, H, W, dtype=torch.int32, device=ro.device)
+            rec_rays = torch.empty(B, H, W, 5, slots, dtype=torch.float32, device=ro.device)
+        elif mode == "bits":
+            hit = torch.empty(B, H, W, (slots + 31) // 32, dtype=torch.int32, device=ro.device)
         L.check(L.lib().mcs_env_shade_fwd(optix_ctx.cpp_wrapper, *[C.byref(x) for x in d], int(BSDF), int(n_samples_x),
                                           int(_rnd_seed) & 0xFFFFFFFF, float(shadow_scale), int(batch_offset),
-                                          diff.data_ptr(), spec.data_ptr(), hit.data_ptr() if hit is not None else None, L.stream_ptr()),
+                                          diff.data_ptr(), spec.data_ptr(), hit.data_ptr() if hit is not None else None,
+                                          rec_cnt.data_ptr() if rec_cnt is not None else None, rec_rays.data_ptr() if rec_rays is not None else None,
+                                          slots, L.stream_ptr()),
                 "optix_env_shade (forward)")
+        ctx.rec = (rec_cnt, rec_rays, slots)
         ctx.save_for_backward(mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms)
         ctx.hit = hit
         ctx.bvh_version = optix_ctx._version
@@ -132,6 +151,14 @@ class _optix_env_shade_func(torch.autograd.Function):
         # replay is only valid against the acceleration structure the forward pass traced (the reference would re-trace whatever
         # BVH the context holds at backward time); if the context was rebuilt in between, fall back to re-tracing
         hit = ctx.hit if (ctx.hit is not None and ctx.bvh_version == optix_ctx._version) else None
+        rec_cnt, rec_rays, slots = ctx.rec
+        if rec_cnt is not None and ctx.bvh_version == optix_ctx._version:
+            dsc = [L.nhwc(gb_pos), L.nhwc(gb_normal), L.nhwc(gb_view_pos), L.nhwc(gb_kd), L.nhwc(gb_ks), L.view_hwc(light)]
+            L.check(L.lib().mcs_env_shade_bwd_replay(*[C.byref(x) for x in dsc], int(ctx.BSDF), int(ctx.n_samples_x), float(ctx.shadow_scale),
+                                                     C.byref(dg), C.byref(sg), rec_cnt.data_ptr(), rec_rays.data_ptr(), int(slots),
+                                                     g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), g[3].data_ptr(), light_grad.data_ptr(),
+                                                     L.stream_ptr()), "optix_env_shade (backward, ray-record replay)")
+            return (None, None, None, g[0], g[1], None, g[2], g[3], light_grad, None, None, None, None, None, None, None, None, None)
         L.check(L.lib().mcs_env_shade_bwd(optix_ctx.cpp_wrapper, *[C.byref(x) for x in d], int(ctx.BSDF), int(ctx.n_samples_x),
                                           int(_rnd_seed) & 0xFFFFFFFF, float(ctx.shadow_scale), int(ctx.batch_offset),
                                           C.byref(dg), C.byref(sg), g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), g[3].data_ptr(),

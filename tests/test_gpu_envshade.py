@@ -133,8 +133,8 @@ def test_errors_are_loud(dev):
 
 
 def test_backward_replays_the_visibility_record(dev):
-    """With a shared seed the backward pass replays the forward pass's hit record instead of re-tracing; both must agree
-    (identical rays, identical bits; only the light-gradient atomics reorder)."""
+    """With a shared seed the backward pass replays what the forward pass recorded -- the evaluated rays ("rays", default) or one
+    visibility bit per sample ("bits") -- instead of re-tracing like the reference (None); all three must agree."""
     import nvdiffrecmc_b200.optixutils as ou
     from nvdiffrecmc_b200.optixutils import ops
     N = 4
@@ -142,7 +142,9 @@ def test_backward_replays_the_visibility_record(dev):
     ctx = _ctx(c, dev)
     perms = _t(c, "perms", dev)
     grads = {}
-    for replay in (True, False):
+    default_mode = ops.HIT_RECORD_REPLAY
+    assert default_mode == "rays"
+    for replay in ("rays", "bits", None):
         ops.HIT_RECORD_REPLAY = replay
         try:
             mask, ro, pos, nrm, view, kd, ks, light, pdf, rows, cols = _args(c, dev)
@@ -152,10 +154,11 @@ def test_backward_replays_the_visibility_record(dev):
             (d.sum() * 0.7 + (s * s).sum()).backward()
             grads[replay] = [x.grad.clone() for x in (pos, nrm, kd, ks, light)]
         finally:
-            ops.HIT_RECORD_REPLAY = True
-    for a, b in zip(grads[True][:4], grads[False][:4]):
-        assert torch.equal(a, b)
-    assert rel_l2(grads[True][4].cpu().numpy(), grads[False][4].cpu().numpy()) < 1e-6
+            ops.HIT_RECORD_REPLAY = default_mode
+    for mode in ("rays", "bits"):
+        for a, b in zip(grads[mode][:4], grads[None][:4]):
+            assert torch.equal(a, b), mode                    # per-pixel gradients: same rays, same order, same arithmetic
+        assert rel_l2(grads[mode][4].cpu().numpy(), grads[None][4].cpu().numpy()) < 1e-6      # env-map gradient: atomics reorder
     # a context rebuilt between forward and backward invalidates the record: the op falls back to re-tracing (no stale replay)
     mask, ro, pos, nrm, view, kd, ks, light, pdf, rows, cols = _args(c, dev)
     light.requires_grad_(True)
