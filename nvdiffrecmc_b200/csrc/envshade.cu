@@ -5,9 +5,11 @@
 // env_shade_bwd (render/optixutils/c_src/torch_bindings.cpp:123-272).
 //
 // B200 mapping (no RT cores, 148 SMs):
-//   * ONE CTA PER SM (32 warps), ONE WARP PER PIXEL, ONE LANE PER SAMPLE, THREE BLOCK-SYNCHRONOUS PHASES PER BATCH OF 32 PIXELS
+//   * FOUR 8-WARP CTAs PER SM, ONE WARP PER PIXEL, ONE LANE PER SAMPLE, THREE CTA-SYNCHRONOUS PHASES PER BATCH OF 8 PIXELS
 //     (history in profiles/: v1 traced inline at 10/32 active lanes; v2 per-warp queues, 13/32 lanes in the while-while loop;
-//      v3 deferred leaf tests, 25/32 lanes but 22 % instruction-fetch stalls with warps spread over all phases):
+//      v3 deferred leaf tests, 25/32 lanes but 22 % instruction-fetch stalls with 32 independent warps spread over all
+//      phases; v4 one 32-warp CTA per SM in lock-step phases: no fetch stalls, L1 hit 88 %; final: 4 CTAs x 8 warps, so that
+//      one CTA's ALU-heavy generate phase overlaps another's latency-heavy trace phase, +9 %):
 //       G  generate: every warp draws the 2N^2 samples of its pixel (exact path, all lanes); rays that can contribute
 //          (n.wi > 0) are ballot-compacted into the warp's segment of a block-wide shared-memory queue (direction, env
 //          texel, MIS weight);
@@ -82,18 +84,29 @@ __device__ __forceinline__ xf uniform_pcg(uint32_t &s)
     return xf((float)(rand_pcg(s) & 0xFFFFFFu) * (1.0f / 16777216.0f));      // exact: division by 2^24
 }
 
-// kernel.cu:140-169; cdf element i at cdf[i*stride]
-__device__ __forceinline__ xf sample_cdf(const float *__restrict__ cdf, int stride, int size, int m, xf x, uint32_t &idx)
+// kernel.cu:140-169; cdf element i at cdf[i*stride].
+// The reference bisects with a fixed iteration count, i.e. 9 DEPENDENT loads at 256 entries -- the top stall of the generate
+// phase (profiles/r01_v4_*).  For a non-decreasing CDF that loop returns exactly min(upper_bound(x), size-1) (first index with
+// cdf[idx] > x; verified exhaustively against the reference loop incl. plateaus and non-power-of-two sizes,
+// tests/test_oracle_core.py::test_cdf_bisection_is_upper_bound), so the same index is found here with a 4-ary search:
+// three independent probes per step, ceil(log4(size)) steps.
+__device__ __forceinline__ xf sample_cdf(const float *__restrict__ cdf, int stride, int size, int steps4, xf x, uint32_t &idx)
 {
     x = xmin(x, xf(0.99999994f));
-    uint32_t lo = 0, hi = (uint32_t)size - 1;
-    for (int i = 0; i < m; ++i) {
-        uint32_t mid = (lo + hi) >> 1;
-        float c = __ldg(cdf + (size_t)mid * stride);
-        lo = x.v >= c ? mid : lo;
-        hi = x.v < c ? mid : hi;
+    int lo = 0, hi = size - 1;                  // answer in [lo, hi]
+    for (int i = 0; i < steps4; ++i) {
+        const int span = hi - lo;
+        const int m1 = lo + (span >> 2), m2 = lo + (span >> 1), m3 = lo + ((3 * span) >> 2);
+        const float c1 = __ldg(cdf + (size_t)m1 * stride), c2 = __ldg(cdf + (size_t)m2 * stride), c3 = __ldg(cdf + (size_t)m3 * stride);
+        if (span > 0) {
+            if (x.v < c1) hi = m1;
+            else if (x.v < c2) { lo = m1 + 1; hi = m2; }
+            else if (x.v < c3) { lo = m2 + 1; hi = m3; }
+            else lo = m3 + 1;
+            lo = min(lo, hi);
+        }
     }
-    idx = hi;
+    idx = (uint32_t)hi;
     xf pdf, sample;
     if (idx == 0) { pdf = xf(__ldg(cdf)); sample = x; }
     else {
@@ -251,11 +264,11 @@ __device__ __forceinline__ float warp_sum(float v)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Block-wide ray queue in shared memory.  One CTA = NW warps = one SM's worth of threads (1 CTA/SM, 64 registers).
+// CTA-wide ray queue in shared memory.  One CTA = NW warps (default 8; 32/NW CTAs per SM, 64 registers/thread).
 // All warps of the CTA move through the three phases TOGETHER (barriers in between):
 //   * the instruction working set at any time is one phase, shared by all resident warps (profiles/r01_v3_*: with warps
 //     spread over G/T/E code, 22 % of all stall samples were instruction-fetch misses);
-//   * the trace phase load-balances over the whole SM: warp w owns segment w of the queue (the live rays of "its" pixel),
+//   * the trace phase load-balances over the CTA: warp w owns segment w of the queue (the live rays of "its" pixel),
 //     drains it first and then steals from the other segments, so no lane idles while any ray of the batch is untraced.
 // Layout is SoA, conflict-free: lane k of a warp touches word k of a segment.  tex bit 31 = "occluded" flag (trace phase).
 // ---------------------------------------------------------------------------------------------
@@ -263,7 +276,7 @@ __device__ __forceinline__ float warp_sum(float v)
 #define MCS_NEAR_FIRST 1
 #endif
 #ifndef MCS_CTA_WARPS
-#define MCS_CTA_WARPS 32
+#define MCS_CTA_WARPS 8
 #endif
 #ifndef MCS_LEAF_BATCH
 #define MCS_LEAF_BATCH 32
@@ -558,7 +571,7 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
 
 // MODE 0: forward, 1: backward, 2: forward + per-ray records
 template <int MODE>
-__global__ void __launch_bounds__(NW * 32, 1) env_shade_kernel(const EnvParams p)
+__global__ void __launch_bounds__(NW * 32, 32 / NW) env_shade_kernel(const EnvParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -585,7 +598,7 @@ __global__ void __launch_bounds__(NW * 32, 1) env_shade_kernel(const EnvParams p
             const int more = q.more_chunks;
             __syncthreads();
             if (have >= NW || !more) break;
-            if (warp < 4) {
+            if (warp < (NW >= 16 ? 4 : 2)) {
                 unsigned int chunk = 0;
                 if (lane == 0) chunk = atomicAdd(p.chunk_counter, 1u);
                 chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
@@ -875,9 +888,10 @@ static int ensure_skip_table(mcs_ctx *c, int N, cudaStream_t s)
 
 static int cdf_iters(int size)
 {
-    // kernel.cu:147  m = int(ceil(log2((float)_max))) + 1
-    unsigned int mx = (unsigned int)size - 1;
-    return (int)ceil(log2((double)(float)mx)) + 1;
+    // 4-ary search: each step shrinks the candidate interval [lo, hi] (span s -> at most s/4 + 1); run until it is a single index
+    int steps = 0;
+    for (int span = size - 1; span > 0; span = span / 4) ++steps;
+    return steps + 1;
 }
 
 static int fill_params(mcs_ctx *ctx, EnvParams &p,

@@ -177,3 +177,48 @@ def test_batch_offset_reproduces_the_full_batch_random_stream():
     other = o.env_shade(c["scene"], c["mask"][s], c["ro"][s], c["pos"][s], c["nrm"][s], c["view"][s], c["kd"][s], c["ks"][s], c["light"], c["pdf"],
                         c["rows"], c["cols"], c["perms"], n_samples_x=N, rnd_seed=9, batch_offset=0)
     assert not np.array_equal(other[0], part[0])
+
+
+def test_cdf_bisection_is_upper_bound():
+    """kernel.cu:144-154 bisects with a fixed iteration count.  For any non-decreasing CDF (plateaus, non-power-of-two sizes) it
+    returns exactly min(upper_bound(x), size-1); the CUDA product relies on this to find the same index with a 4-ary search."""
+    rng = np.random.default_rng(0)
+
+    def ref(cdf, x):
+        lo, hi = 0, len(cdf) - 1
+        m = int(math.ceil(math.log2(np.float32(hi)))) + 1
+        for _ in range(m):
+            mid = (lo + hi) // 2
+            if x >= cdf[mid]:
+                lo = mid
+            if x < cdf[mid]:
+                hi = mid
+        return hi
+
+    def four_ary(cdf, x):             # integer logic of csrc/envshade.cu:sample_cdf
+        lo, hi = 0, len(cdf) - 1
+        steps, span = 1, len(cdf) - 1
+        while span > 0:
+            steps += 1; span //= 4
+        for _ in range(steps):
+            span = hi - lo
+            m1, m2, m3 = lo + (span >> 2), lo + (span >> 1), lo + ((3 * span) >> 2)
+            if span > 0:
+                if x < cdf[m1]: hi = m1
+                elif x < cdf[m2]: lo, hi = m1 + 1, m2
+                elif x < cdf[m3]: lo, hi = m2 + 1, m3
+                else: lo = m3 + 1
+                lo = min(lo, hi)
+        return hi
+    for _ in range(400):
+        n = int(rng.choice([2, 3, 5, 16, 17, 31, 32, 100, 256, 257, 1000, 1024, 2048]))
+        p = rng.random(n) ** rng.choice([1, 4, 16])
+        if rng.random() < 0.5:
+            p[rng.random(n) < 0.3] = 0
+        if p.sum() == 0:
+            p[0] = 1
+        cdf = np.cumsum(p.astype(np.float32), dtype=np.float32); cdf = (cdf / cdf[-1]).astype(np.float32)
+        for x in np.concatenate([rng.random(12).astype(np.float32), cdf[rng.integers(0, n, 4)], [np.float32(0), np.float32(0.99999994)]]):
+            x = min(np.float32(x), np.float32(0.99999994))
+            ub = min(int(np.searchsorted(cdf, x, side="right")), n - 1)
+            assert ref(cdf, x) == ub == four_ary(cdf, x)
