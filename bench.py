@@ -83,6 +83,17 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def build_scene_numpy(wl, rank):
     from nvdiffrecmc_b200 import synth
+    if wl["mesh"] == "grid1m":          # BASELINE configs[4]-like: ~1M triangles (displaced height field with an overhang ring)
+        n = 724
+        g = np.linspace(-1, 1, n + 1, dtype=np.float32)
+        X, Z = np.meshgrid(g, g, indexing="ij")
+        Y = (0.25 * np.sin(7 * X) * np.cos(5 * Z) - 0.2).astype(np.float32)
+        v = np.stack([X, Y, Z], -1).reshape(-1, 3)
+        idx = np.arange((n + 1) * (n + 1)).reshape(n + 1, n + 1)
+        a, b, c, d = idx[:-1, :-1], idx[1:, :-1], idx[1:, 1:], idx[:-1, 1:]
+        f = np.concatenate([np.stack([a, c, b], -1).reshape(-1, 3), np.stack([a, d, c], -1).reshape(-1, 3)]).astype(np.int32)
+        v, f = synth.merge((v, f), synth.torus_mesh(R=0.6, r=0.08, nu=256, nv=64, tilt=0.3))
+        return v, f, synth.vertex_normals(v, f)
     v, f = synth.scene_mesh(wl["mesh"], level=wl["mesh_level"], seed=5)
     vn = synth.vertex_normals(v, f)
     return v, f, vn
@@ -344,6 +355,9 @@ def main():
     ap.add_argument("--impl", default="mcshade", choices=["mcshade", "reference"])
     ap.add_argument("--views", type=int, default=None, help="override views per GPU (debug)")
     ap.add_argument("--res", type=int, default=None, help="override resolution (debug)")
+    ap.add_argument("--n", type=int, default=None, help="override n_samples_x (debug)")
+    ap.add_argument("--mesh", default=None, help="override mesh: blob | blob+torus | full | grid1m (debug)")
+    ap.add_argument("--level", type=int, default=None, help="override icosphere subdivision level (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = dict(WORKLOAD)
@@ -351,6 +365,14 @@ def main():
         wl["views_per_gpu"] = args.views
     if args.res:
         wl["res"] = args.res
+    if args.n:
+        wl["n_samples_x"] = args.n
+    if args.mesh:
+        wl["mesh"] = args.mesh
+    if args.level is not None:
+        wl["mesh_level"] = args.level
+    if args.views or args.res or args.n or args.mesh or args.level is not None:
+        wl["name"] = "DEBUG OVERRIDE of " + wl["name"]
     if args.impl == "reference":
         return run_reference(args, wl)
 
