@@ -272,6 +272,9 @@ __device__ __forceinline__ float warp_sum(float v)
 //     drains it first and then steals from the other segments, so no lane idles while any ray of the batch is untraced.
 // Layout is SoA, conflict-free: lane k of a warp touches word k of a segment.  tex bit 31 = "occluded" flag (trace phase).
 // ---------------------------------------------------------------------------------------------
+#ifndef MCS_POLL_AFTER_BATCH
+#define MCS_POLL_AFTER_BATCH 1
+#endif
 #ifndef MCS_NEAR_FIRST
 #define MCS_NEAR_FIRST 1
 #endif
@@ -523,7 +526,9 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
             bool hasA = false, hasB = false;
             int leafA = 0, leafB = 0;
             const int cur = my;
+#if !MCS_POLL_AFTER_BATCH
             if (my >= 0 && (q.tex[my] >> 31)) my = -1;      // a deferred leaf test already found an occluder
+#endif
             if (my >= 0) {
                 const float4 *n = b.nodes + 4 * (size_t)node;
                 const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
@@ -565,6 +570,11 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
             nact = __popc(__ballot_sync(0xFFFFFFFFu, my >= 0));
         } while (pend < LEAF_BATCH && nact >= thresh);
         while (pend >= LEAF_BATCH) leaf_batch(32);
+#if MCS_POLL_AFTER_BATCH
+        // occluded bits of this warp's rays only change inside leaf_batch (a ray is walked and leaf-tested by one warp):
+        // poll here instead of once per node step
+        if (my >= 0 && (q.tex[my] >> 31)) my = -1;
+#endif
     }
     __syncwarp();
 }
