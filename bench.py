@@ -150,6 +150,12 @@ class GpuWorkload:
         self.light_base.grad = self.flat_grad[:n_light].view_as(self.light_base)
         self.kd_tex.grad = self.flat_grad[n_light:n_light + n_tex].view_as(self.kd_tex)
         self.ks_tex.grad = self.flat_grad[n_light + n_tex:].view_as(self.ks_tex)
+        # Adam over the flat bucket (train.py:401-409 uses torch.optim.Adam per parameter group; one fused launch here), then the
+        # post-step clamps of train.py:455-461 / material ranges of configs/*.json
+        self.flat_param = torch.nn.Parameter(self.flat, requires_grad=False)
+        self.flat_param.grad = self.flat_grad
+        self.optimizer = torch.optim.Adam([self.flat_param], lr=wl.get("lr", 0.01), fused=True)
+        self.n_light = n_light
         self.lgt = EnvironmentLight(self.light_base)
         self.denoiser = BilateralDenoiser(influence=wl["sigma"] / 2.0)
         self.perms = torch.tensor(synth.make_perms(N, seed=3), device=dev)
@@ -197,6 +203,10 @@ class GpuWorkload:
         if self.world > 1:
             torch.distributed.all_reduce(self.flat_grad)                             # ONE collective per step
             self.flat_grad.div_(self.world)
+        self.optimizer.step()                                                        # train.py:452
+        with torch.no_grad():
+            self.flat[:self.n_light].clamp_(min=0.0)                                 # light.clamp_(min=0), train.py:460
+            self.flat[self.n_light:].clamp_(0.0, 1.0)                                # material kd / ks ranges
         return loss
 
 
@@ -310,7 +320,7 @@ def host_cores():
             n = max(1, min(n, int(float(q) / float(per) + 0.5)))
     except Exception:
         pass
-    os.environ.setdefault("OMP_NUM_THREADS", str(n))
+    os.environ["OMP_NUM_THREADS"] = str(n)          # torchrun exports 1; the oracle legs also call Oracle.set_threads(n)
     return n
 
 
@@ -322,6 +332,7 @@ def run_reference(args, wl):
     cores = host_cores()
     from common import make_case, oracle
     o = oracle()
+    cores = o.set_threads(cores)
     N, res_s = wl["n_samples_x"], 128
     case = make_case(res=res_s, B=1, N=N, mesh=wl["mesh"], level=wl["mesh_level"], light="random", light_hw=(wl["light_res"], wl["light_res"]),
                      perm_rows=4096)
@@ -518,6 +529,7 @@ def main():
         ncores = host_cores()
         from common import make_case, oracle
         o = oracle()
+        ncores = o.set_threads(ncores)
         res_s = 96
         case = make_case(res=res_s, B=1, N=N, mesh=wl["mesh"], level=wl["mesh_level"], light="random", light_hw=(wl["light_res"], wl["light_res"]),
                          perm_rows=4096)

@@ -137,6 +137,12 @@ class Oracle:
         assert self.lib.orc_sizeof_envshade() == C.sizeof(self._ES), "struct layout mismatch"
 
     # ------------------------------------------------------------------ helpers
+    def set_threads(self, n):
+        """OpenMP team size of the oracle's parallel loops.  Called explicitly because OMP_NUM_THREADS is only read when libgomp
+        initialises (torch has usually loaded it already) and torchrun exports OMP_NUM_THREADS=1.  Returns the size in effect."""
+        self.lib.omp_set_num_threads(int(n))
+        return int(self.lib.omp_get_max_threads())
+
     def _a(self, x, shape=None):
         x = np.ascontiguousarray(np.asarray(x, dtype=self.dt))
         if shape is not None:
