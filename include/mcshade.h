@@ -190,6 +190,12 @@ int mcs_image_loss_bwd(const mcs_tensor *img, const mcs_tensor *target, int32_t 
 int mcs_xfm_fwd(const mcs_tensor *points, const mcs_tensor *matrix, int32_t is_points, float *out, mcs_stream s);
 int mcs_xfm_bwd(const mcs_tensor *points, const mcs_tensor *matrix, const mcs_tensor *d_out, int32_t is_points, float *d_points, mcs_stream s);
 
+/* ---- env-light pdf / CDF tables: replaces the torch-op chain of EnvironmentLight.update_pdf,
+ *      render/light.py:46-59.  base: (1, Hl, Wl, 3) view.  Outputs (caller-allocated, contiguous): pdf [Hl,Wl] normalised to sum 1,
+ *      rows [Hl] (what the call site passes as lgt.rows[:,0], render/render.py:114), cols [Hl,Wl]; row_totals: Hl doubles of scratch
+ *      (holds the un-normalised row sums on return).  Sums are carried in fp64 and rounded once. */
+int mcs_update_pdf(const mcs_tensor *base, float *pdf, float *rows, float *cols, double *row_totals, mcs_stream s);
+
 #ifdef __cplusplus
 }
 #endif
