@@ -239,6 +239,81 @@ __global__ void __launch_bounds__(256) k_emit_nodes(int T, const int32_t *__rest
     nodes[4 * (size_t)i + 3] = make_float4(__int_as_float(child_code(c0, T, range)), __int_as_float(child_code(c1, T, range)), 0.0f, 0.0f);
 }
 
+// Quantised copy of the traversal nodes for the shadow rays.  The fused kernel's trace loop is bound by the L1 wavefront queue
+// (every divergent 128-bit load costs one wavefront per distinct line, ~2 cycles each; profiles/r01_v5_*), i.e. by the NUMBER
+// of load instructions per node visit, not by bytes or arithmetic.  A node with both child boxes as 16-bit integers on ONE
+// scene-wide grid is 2 x 16 bytes -- one load per child instead of four per node:
+//   uint4 child = { lo.x | hi.x << 16,  lo.y | hi.y << 16,  lo.z | hi.z << 16,  child code }
+// Grid: origin = root box min, cell = smallest power of two with 65532 cells covering the root extent (per axis), so
+// cell * (1/d) is exact and the decode is one byte-permute + one FMA per plane (envshade.cu:trace_queue).  Boxes are rounded
+// outward and inflated by two more cells per side, which covers the quantisation rounding and the <= 1-cell error of the
+// biased decode: culling stays conservative, the visibility result is unchanged (tests/test_gpu_envshade.py records test).
+__global__ void __launch_bounds__(256) k_emit_nodesq(int T, const int32_t *__restrict__ left, const int32_t *__restrict__ right,
+                                                     const int2 *__restrict__ range, const float *__restrict__ lo, const float *__restrict__ hi,
+                                                     uint4 *__restrict__ nodesq, uint4 *__restrict__ nodesq4, float *__restrict__ qgrid)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float org[3], inv_cell[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        org[a] = lo[a];                                                      // node 0 = root (for T == 1: the only leaf)
+        const float ext = __fsub_rn(hi[a], lo[a]);
+        // smallest power of two >= ext / 65532 (exponent arithmetic: no rounding in the grid itself)
+        int e;
+        const float m = frexpf(fmaxf(ext, 1e-30f) * (1.0f / 65532.0f), &e);  // value = m * 2^e, m in [0.5, 1)
+        const int k = (m == 0.5f) ? e - 1 : e;
+        inv_cell[a] = ldexpf(1.0f, -k);
+        if (i == 0) { qgrid[a] = org[a]; qgrid[3 + a] = ldexpf(1.0f, k); }
+    }
+    const bool tiny = T <= MCS_LEAF_MAX;
+    if (tiny ? i != 0 : i >= T - 1) return;
+    int cn[2], code[2];
+    if (tiny) { cn[0] = 0; cn[1] = -1; code[0] = ~((0 << 3) | (T - 1)); code[1] = ~0; }
+    else { cn[0] = left[i]; cn[1] = right[i]; code[0] = child_code(cn[0], T, range); code[1] = child_code(cn[1], T, range); }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t ql[3], qh[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (cn[c] < 0) { ql[a] = 65535u; qh[a] = 0u; continue; }          // unused slot: inverted box, entry > exit for every ray
+            const float fl = floorf(__fmul_rn(__fsub_rn(lo[3 * (size_t)cn[c] + a], org[a]), inv_cell[a])) - 2.0f;
+            const float fh = ceilf(__fmul_rn(__fsub_rn(hi[3 * (size_t)cn[c] + a], org[a]), inv_cell[a])) + 2.0f;
+            ql[a] = (uint32_t)fminf(fmaxf(fl, 0.0f), 65535.0f);
+            qh[a] = (uint32_t)fminf(fmaxf(fh, 0.0f), 65535.0f);
+        }
+        nodesq[2 * (size_t)i + c] = make_uint4(ql[0] | (qh[0] << 16), ql[1] | (qh[1] << 16), ql[2] | (qh[2] << 16), (uint32_t)code[c]);
+    }
+    // 4-wide view: node i holds the (up to four) GRANDCHILDREN of binary node i -- a child that is a leaf run stays one slot, an
+    // internal child is replaced by its two children.  Same index space as the binary nodes (no allocation; nodes on odd levels
+    // are never referenced).  A ray visits ~half as many nodes (13.8 vs 28.8 on the benchmark mesh) and tests fewer boxes (52 vs 58).
+    // Unused slots are inverted boxes (lo = 65535, hi = 0): with sign-selected planes entry > exit for every ray.
+    int gn[4] = {-1, -1, -1, -1}, gcode[4] = {~0, ~0, ~0, ~0}, ng = 0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (cn[c] < 0) continue;
+        if (code[c] < 0) { gn[ng] = cn[c]; gcode[ng] = code[c]; ++ng; }
+        else {
+            const int g0 = left[cn[c]], g1 = right[cn[c]];
+            gn[ng] = g0; gcode[ng] = child_code(g0, T, range); ++ng;
+            gn[ng] = g1; gcode[ng] = child_code(g1, T, range); ++ng;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t ql[3] = {65535u, 65535u, 65535u}, qh[3] = {0u, 0u, 0u};
+        if (gn[c] >= 0) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float fl = floorf(__fmul_rn(__fsub_rn(lo[3 * (size_t)gn[c] + a], org[a]), inv_cell[a])) - 2.0f;
+                const float fh = ceilf(__fmul_rn(__fsub_rn(hi[3 * (size_t)gn[c] + a], org[a]), inv_cell[a])) + 2.0f;
+                ql[a] = (uint32_t)fminf(fmaxf(fl, 0.0f), 65535.0f);
+                qh[a] = (uint32_t)fminf(fmaxf(fh, 0.0f), 65535.0f);
+            }
+        }
+        nodesq4[4 * (size_t)i + c] = make_uint4(ql[0] | (qh[0] << 16), ql[1] | (qh[1] << 16), ql[2] | (qh[2] << 16), (uint32_t)gcode[c]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Collapse of the binary LBVH into the 8-wide compressed layout (bvh8.cuh).  Top-down, level by level inside ONE CTA
 // (the number of wide nodes is ~T/4.5; at 7k triangles this is ~2 us per level, at 1M triangles ~0.3 ms in total):
@@ -403,7 +478,7 @@ int mcs_ctx_destroy(mcs_ctx *c)
 {
     if (!c) return 0;
     DevBuf *bufs[] = {&c->bounds, &c->tlo, &c->thi, &c->keys, &c->keys_alt, &c->vals, &c->vals_alt, &c->left, &c->right, &c->parent,
-                      &c->lo, &c->hi, &c->flags, &c->range, &c->sort_tmp, &c->nodes, &c->tris, &c->nodes8, &c->tris8, &c->wide_bin, &c->lcg_skip, &c->light_grad4};
+                      &c->lo, &c->hi, &c->flags, &c->range, &c->sort_tmp, &c->nodes, &c->tris, &c->nodesq, &c->nodesq4, &c->qgrid, &c->nodes8, &c->tris8, &c->wide_bin, &c->lcg_skip, &c->light_grad4};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     delete c;
@@ -435,6 +510,9 @@ int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris
     if (int e = mcs_buf_reserve(c->range, nT * sizeof(int2), s)) return e;
     if (int e = mcs_buf_reserve(c->nodes, nT * 4 * sizeof(float4), s)) return e;
     if (int e = mcs_buf_reserve(c->tris, nT * 3 * sizeof(float4), s)) return e;
+    if (int e = mcs_buf_reserve(c->nodesq, nT * 2 * sizeof(uint4), s)) return e;
+    if (int e = mcs_buf_reserve(c->nodesq4, nT * 4 * sizeof(uint4), s)) return e;
+    if (int e = mcs_buf_reserve(c->qgrid, 8 * sizeof(float), s)) return e;
 #if MCS_BVH8
     if (int e = mcs_buf_reserve(c->nodes8, nT * 5 * sizeof(float4), s)) return e;
     if (int e = mcs_buf_reserve(c->tris8, nT * 3 * sizeof(float4), s)) return e;
@@ -469,6 +547,9 @@ int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris
     k_emit_nodes<<<nblk(T > 1 ? T - 1 : 1, 256), 256, 0, s>>>(T, (const int32_t *)c->left.p, (const int32_t *)c->right.p, (const int2 *)c->range.p,
                                                               (const float *)c->lo.p, (const float *)c->hi.p, (float4 *)c->nodes.p);
     MCS_LAUNCH_CHECK();
+    k_emit_nodesq<<<nblk(T > 1 ? T - 1 : 1, 256), 256, 0, s>>>(T, (const int32_t *)c->left.p, (const int32_t *)c->right.p, (const int2 *)c->range.p,
+                                                               (const float *)c->lo.p, (const float *)c->hi.p, (uint4 *)c->nodesq.p, (uint4 *)c->nodesq4.p, (float *)c->qgrid.p);
+    MCS_LAUNCH_CHECK();
 #if MCS_BVH8
     k_build_wide<<<1, 1024, 0, s>>>(T, (const int32_t *)c->left.p, (const int32_t *)c->right.p, (const int2 *)c->range.p, (const float *)c->lo.p,
                                     (const float *)c->hi.p, (const float4 *)c->tris.p, (float4 *)c->nodes8.p, (float4 *)c->tris8.p, (int *)c->wide_bin.p);
@@ -502,7 +583,7 @@ int mcs_trace_visibility(mcs_ctx *c, const float *ro, const float *rd, int64_t n
 #if MCS_BVH8
     VisView b{(const float4 *)c->nodes8.p, (const float4 *)c->tris8.p};
 #else
-    VisView b{(const float4 *)c->nodes.p, (const float4 *)c->tris.p};
+    VisView b{(const float4 *)c->nodes.p, (const float4 *)c->tris.p, nullptr, nullptr, nullptr};
 #endif
     k_visibility<<<nblk(n, 128), 128, 0, (cudaStream_t)stream>>>(b, ro, rd, n, vis);
     MCS_LAUNCH_CHECK();
@@ -514,7 +595,7 @@ int mcs_trace_closest(mcs_ctx *c, const float *ro, const float *rd, int64_t n, i
     MCS_REQUIRE(c && c->T > 0, "mcs_trace_closest: no acceleration structure built (call mcs_bvh_build first)");
     MCS_REQUIRE(n >= 0 && (n == 0 || (ro && rd && tri_id && tuv)), "mcs_trace_closest: bad arguments");
     if (n == 0) return 0;
-    BvhView b{(const float4 *)c->nodes.p, (const float4 *)c->tris.p};
+    BvhView b{(const float4 *)c->nodes.p, (const float4 *)c->tris.p, nullptr, nullptr, nullptr};
     k_closest<<<nblk(n, 128), 128, 0, (cudaStream_t)stream>>>(b, ro, rd, n, tri_id, tuv);
     MCS_LAUNCH_CHECK();
     return 0;

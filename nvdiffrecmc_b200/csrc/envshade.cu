@@ -272,17 +272,11 @@ __device__ __forceinline__ float warp_sum(float v)
 //     drains it first and then steals from the other segments, so no lane idles while any ray of the batch is untraced.
 // Layout is SoA, conflict-free: lane k of a warp touches word k of a segment.  tex bit 31 = "occluded" flag (trace phase).
 // ---------------------------------------------------------------------------------------------
-#ifndef MCS_POLL_AFTER_BATCH
-#define MCS_POLL_AFTER_BATCH 1
-#endif
-#ifndef MCS_NEAR_FIRST
-#define MCS_NEAR_FIRST 1
-#endif
-#ifndef MCS_BRANCHFREE
-#define MCS_BRANCHFREE 1                 // descend / push / pop with selects instead of a branch ladder (+1 %)
-#endif
 #ifndef MCS_REPLAY_MINB
 #define MCS_REPLAY_MINB 3                // replay kernel: 80 registers, 3 CTAs/SM (2.93 -> 2.54 ms on 4 views; 4 CTAs/SM spills, software prefetch was slower)
+#endif
+#ifndef MCS_WIDE4
+#define MCS_WIDE4 1                      // shadow rays walk the 4-wide view of the quantised nodes (64 B, half the visits)
 #endif
 #ifndef MCS_CTA_WARPS
 #define MCS_CTA_WARPS 8
@@ -296,7 +290,7 @@ __device__ __forceinline__ float warp_sum(float v)
 constexpr int NW = MCS_CTA_WARPS;
 constexpr int SEG = 128;                 // queue entries per warp segment (= one pixel at N = 8)
 constexpr int QTOT = NW * SEG;
-constexpr int PCAP = 128;                // pending (ray, leaf) pairs per warp: < 32 carried over + at most 64 appended per node step
+constexpr int PCAP = MCS_WIDE4 ? 160 : 96;   // pending (ray, leaf) pairs per warp: < 32 carried over + at most 64 (binary) / 128 (4-wide) appended per node step
 constexpr int PIXRING = 256;
 static_assert(QTOT <= 65536, "queue entry index is stored in 16 bits");
 static_assert(SEG <= 256 && SEG % 32 == 0, "sample slot within a fill is stored in 8 bits");
@@ -307,8 +301,7 @@ struct BlockQueue {
     uint16_t vlist[QTOT];                // per segment: dense list of entries that reach the eval phase
     uint8_t qitem[QTOT];                 // sample slot of the entry within the current queue fill (w - w0 < SEG)
     uint32_t hitw[NW][SEG / 32];         // per segment: occluded bits of the current queue fill
-    uint16_t pl_ray[NW][PCAP];           // per warp: deferred leaf tests, queue entry ...
-    int pl_leaf[NW][PCAP];               // ... and leaf code
+    uint2 pl[NW][PCAP];                  // per warp: deferred leaf tests, x = queue entry, y = leaf code
     float ro[NW][3];                     // per segment: ray origin / view vector / pixel id / live-ray count / fetch cursor
     float wo[NW][3];
     int pixid[NW];
@@ -458,30 +451,80 @@ __device__ __forceinline__ void gen_segment(const EnvParams &p, BlockQueue &q, B
 //   * visibility of a ray = its occluded bit after all segments AND all pending lists have drained (block barrier).
 // (An 8-wide compressed BVH, bvh8.cuh, was measured too: it removes the L2 round trips but its unrolled node test is
 //  instruction-fetch bound and ended up 15 % slower; profiles/r01_bvh8_*.)
+// Per-ray constants of the quantised node test (bvh.cu:k_emit_nodesq): plane t = (origin + q * cell - o) / d = q' * A + B with
+// q' = 2^23 + q (the float whose low mantissa bits are the 16-bit coordinate), A = cell / d (exact: cell is a power of two),
+// B = (origin - o) / d - 2^23 * A.  |error| < 0.51 cell (rounding of B), covered by the two-cell inflation of the stored boxes.
+// The byte-permute that builds q' also picks the entry / exit plane from the (lo | hi << 16) word: its selector depends on the
+// sign of d only, so the slab test needs no min/max per axis.  Zero direction components are nudged to +-1e-20 (keeps 2^23 * A
+// finite for any sane scene; same conservative argument as ray_pre's 1e-30).
+struct RayQ {
+    float ax, ay, az, bx, by, bz;
+    uint32_t nx, ny, nz;             // PRMT selectors of the entry plane (0x7410 = low half, 0x7432 = high half); exit = ^ 0x0022
+};
+__device__ __forceinline__ RayQ rayq_pre(const float *__restrict__ g, f3 o, f3 d)
+{
+    const float dx = fabsf(d.x) < 1e-20f ? copysignf(1e-20f, d.x) : d.x;
+    const float dy = fabsf(d.y) < 1e-20f ? copysignf(1e-20f, d.y) : d.y;
+    const float dz = fabsf(d.z) < 1e-20f ? copysignf(1e-20f, d.z) : d.z;
+    const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
+    RayQ r;
+    r.ax = __ldg(g + 3) * ix; r.ay = __ldg(g + 4) * iy; r.az = __ldg(g + 5) * iz;
+    r.bx = __fmaf_rn(-8388608.0f, r.ax, __fmul_rn(__fsub_rn(__ldg(g), o.x), ix));
+    r.by = __fmaf_rn(-8388608.0f, r.ay, __fmul_rn(__fsub_rn(__ldg(g + 1), o.y), iy));
+    r.bz = __fmaf_rn(-8388608.0f, r.az, __fmul_rn(__fsub_rn(__ldg(g + 2), o.z), iz));
+    r.nx = dx < 0.0f ? 0x7432u : 0x7410u; r.ny = dy < 0.0f ? 0x7432u : 0x7410u; r.nz = dz < 0.0f ? 0x7432u : 0x7410u;
+    return r;
+}
+__device__ __forceinline__ float qplane(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)); }
+__device__ __forceinline__ bool qslab(const uint4 c, const RayQ &r, float &tn)
+{
+    const float a0 = fmaf(qplane(c.x, r.nx), r.ax, r.bx), a1 = fmaf(qplane(c.x, r.nx ^ 0x22u), r.ax, r.bx);
+    const float b0 = fmaf(qplane(c.y, r.ny), r.ay, r.by), b1 = fmaf(qplane(c.y, r.ny ^ 0x22u), r.ay, r.by);
+    const float c0 = fmaf(qplane(c.z, r.nz), r.az, r.bz), c1 = fmaf(qplane(c.z, r.nz ^ 0x22u), r.az, r.bz);
+    tn = fmaxf(fmaxf(a0, b0), fmaxf(c0, 0.0f));
+    const float tf = fminf(fminf(a1, b1), fminf(c1, MCS_TMAX));
+    return tn <= tf * 1.0000004f;
+}
+
+// ---- phase T: any-hit traversal of all queued rays of the CTA: work stealing + dynamic fetch + deferred leaf tests ----
+// SIMT-friendly organisation (profiles/r01_v2_*: a classic while-while loop ran at 13/32 lanes because lanes wait for each
+// other at every leaf):
+//   * node loop: every busy lane performs exactly one node step per iteration (fetch the 32-byte quantised node: one 128-bit
+//     load per child, two slab tests, descend / push / pop).  Leaf children that pass the slab test are NOT intersected here:
+//     the (ray, leaf run) pair is appended to the warp's pending list (ballot compaction) and the lane keeps walking,
+//     speculating that the leaf misses;
+//   * as soon as 32 pairs are pending the warp intersects them with all lanes busy; a hit sets the ray's "occluded" bit
+//     (tex bit 31), which the owning lane polls after each batch to abandon the walk;
+//   * a lane whose walk ends pulls the next ray -- from the warp's own segment first, then from the other warps' segments --
+//     as soon as fewer than REFILL_BELOW lanes are busy;
+//   * visibility of a ray = its occluded bit after all segments AND all pending lists have drained (block barrier).
+// What bounds it (profiles/r01_v6_*): instruction issue.  With fp32 64-byte nodes (4 loads per visit) the L1 data pipe was a
+// co-limiter at 75 %; the quantised nodes took it to 47 % and long-scoreboard stalls from 25 % to 18 %.  A 4-wide fp32 node
+// (half the visits, 7 loads each) and fetching through the texture path were measured and were slower / equal; an 8-wide
+// compressed node (bvh8.cuh) costs more instructions per ray than it saves.
 __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, const int warp, const int lane)
 {
     constexpr int REFILL_BELOW = MCS_REFILL_BELOW;
     constexpr int LEAF_BATCH = MCS_LEAF_BATCH;
-    constexpr int DONE = 0x7FFFFFFF;
     const unsigned lt = (1u << lane) - 1u;
     int pend = 0;
     int my = -1;
-    int node = DONE, sp = 0;
-    int stack[MCS_STACK];
-    RayPre r = ray_pre(F3(0.0f), F3(1.0f));
+    int node = 0, sp = 0;
+    int stack[MCS_WIDE4 ? 96 : MCS_STACK];       // 4-wide: up to 3 pushes per visit (1.5 per binary level)
+    RayQ r; r.ax = r.ay = r.az = 1.0f; r.bx = r.by = r.bz = 0.0f; r.nx = r.ny = r.nz = 0x7410u;
     const BvhView b = p.bvh;
-    uint16_t *pl_ray = q.pl_ray[warp];
-    int *pl_leaf = q.pl_leaf[warp];
+    uint2 *pl = q.pl[warp];
     int seg = warp, exhausted = 0;           // segment being drained, number of segments found empty so far
 
     auto leaf_batch = [&](int n) {
-        // intersect the last n (<= 32) pending pairs, one per lane
+        // intersect the last n (<= 32) pending (ray, leaf run) pairs, one per lane
         __syncwarp();
         const int base = pend - n;
         if (lane < n) {
-            const int e = pl_ray[base + lane];
+            const uint2 ent = pl[base + lane];
+            const int e = (int)ent.x;
             if (!(q.tex[e] >> 31)) {
-                const int code = ~pl_leaf[base + lane];
+                const int code = ~(int)ent.y;
                 const int start = code >> 3, cnt = (code & 7) + 1;
                 const int ps = e / SEG;
                 const f3 o = F3(q.ro[ps][0], q.ro[ps][1], q.ro[ps][2]);
@@ -515,7 +558,7 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
             if (my < 0 && rank < take) {
                 const int idx = seg * SEG + base + rank;
                 my = idx;
-                r = ray_pre(F3(q.ro[seg][0], q.ro[seg][1], q.ro[seg][2]), F3(q.dx[idx], q.dy[idx], q.dz[idx]));
+                r = rayq_pre(b.qgrid, F3(q.ro[seg][0], q.ro[seg][1], q.ro[seg][2]), F3(q.dx[idx], q.dy[idx], q.dz[idx]));
                 node = 0; sp = 0;
             }
             if (take < need) { seg = seg + 1 == NW ? 0 : seg + 1; ++exhausted; }
@@ -529,68 +572,78 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
         }
         const int thresh = exhausted < NW ? REFILL_BELOW : 1;
         do {
-            bool hasA = false, hasB = false;
-            int leafA = 0, leafB = 0;
+#if MCS_WIDE4
             const int cur = my;
-#if !MCS_POLL_AFTER_BATCH
-            if (my >= 0 && (q.tex[my] >> 31)) my = -1;      // a deferred leaf test already found an occluder
-#endif
+            unsigned lmask = 0u;
+            int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
             if (my >= 0) {
-                const float4 *n = b.nodes + 4 * (size_t)node;
-                const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
-                float a0 = fmaf(q0.x, r.ix, -r.ox), a1 = fmaf(q0.y, r.ix, -r.ox);
-                float b0 = fmaf(q0.z, r.iy, -r.oy), b1 = fmaf(q0.w, r.iy, -r.oy);
-                float c0 = fmaf(q2.x, r.iz, -r.oz), c1 = fmaf(q2.y, r.iz, -r.oz);
-                const float tn0 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
-                const float tf0 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), MCS_TMAX));
-                a0 = fmaf(q1.x, r.ix, -r.ox); a1 = fmaf(q1.y, r.ix, -r.ox);
-                b0 = fmaf(q1.z, r.iy, -r.oy); b1 = fmaf(q1.w, r.iy, -r.oy);
-                c0 = fmaf(q2.z, r.iz, -r.oz); c1 = fmaf(q2.w, r.iz, -r.oz);
-                const float tn1 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
-                const float tf1 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), MCS_TMAX));
-                const bool h0 = tn0 <= tf0 * 1.0000004f, h1 = tn1 <= tf1 * 1.0000004f;
-                const int ch0 = __float_as_int(q3.x), ch1 = __float_as_int(q3.y);
-                hasA = h0 && ch0 < 0; leafA = ch0;
-                hasB = h1 && ch1 < 0; leafB = ch1;
+                const uint4 *n = b.nodesq4 + 4 * (size_t)node;
+                const uint4 k0 = __ldg(n), k1 = __ldg(n + 1), k2 = __ldg(n + 2), k3 = __ldg(n + 3);
+                float tn;
+                const bool h0 = qslab(k0, r, tn), h1 = qslab(k1, r, tn), h2 = qslab(k2, r, tn), h3 = qslab(k3, r, tn);
+                c0 = (int)k0.w; c1 = (int)k1.w; c2 = (int)k2.w; c3 = (int)k3.w;
+                const bool p0 = h0 && c0 >= 0, p1 = h1 && c1 >= 0, p2 = h2 && c2 >= 0, p3 = h3 && c3 >= 0;
+                lmask = (h0 && c0 < 0 ? 1u : 0u) | (h1 && c1 < 0 ? 2u : 0u) | (h2 && c2 < 0 ? 4u : 0u) | (h3 && c3 < 0 ? 8u : 0u);
+                // internal children hit: push them all (predicated stores; any-hit: the order does not change the result), continue
+                // with the last one straight from its register (its stack slot is released again); nothing hit -> pop
+                if (p0) stack[sp] = c0;
+                sp += p0 ? 1 : 0;
+                if (p1) stack[sp] = c1;
+                sp += p1 ? 1 : 0;
+                if (p2) stack[sp] = c2;
+                sp += p2 ? 1 : 0;
+                if (p3) stack[sp] = c3;
+                sp += p3 ? 1 : 0;
+                if (p0 || p1 || p2 || p3) { node = p3 ? c3 : (p2 ? c2 : (p1 ? c1 : c0)); --sp; }
+                else if (sp) node = stack[--sp];
+                else my = -1;                               // walk finished; verdict comes from the occluded bit
+            }
+            // defer the leaf tests: one (ray, leaf run) pair per leaf child hit, one ballot round per pair of the busiest lane
+            for (unsigned mL = __ballot_sync(0xFFFFFFFFu, lmask != 0u); mL; mL = __ballot_sync(0xFFFFFFFFu, lmask != 0u)) {
+                if (lmask) {
+                    const int c = __ffs(lmask) - 1;
+                    pl[pend + __popc(mL & lt)] = make_uint2((unsigned)cur, (unsigned)(c == 0 ? c0 : (c == 1 ? c1 : (c == 2 ? c2 : c3))));
+                    lmask &= lmask - 1u;
+                }
+                pend += __popc(mL);
+            }
+#else
+            const int cur = my;
+            unsigned lmask = 0u;
+            int ch0 = 0, ch1 = 0;
+            if (my >= 0) {
+                const uint4 *n = b.nodesq + 2 * (size_t)node;
+                const uint4 k0 = __ldg(n), k1 = __ldg(n + 1);
+                float tn0, tn1;
+                const bool h0 = qslab(k0, r, tn0), h1 = qslab(k1, r, tn1);
+                ch0 = (int)k0.w; ch1 = (int)k1.w;
+                lmask = (h0 && ch0 < 0 ? 1u : 0u) | (h1 && ch1 < 0 ? 2u : 0u);
+                // descend / push / pop with selects; the nearer internal child first (occluders close to the origin end the ray early)
                 const bool i0 = h0 && ch0 >= 0, i1 = h1 && ch1 >= 0;
-#if MCS_BRANCHFREE
                 const bool both = i0 && i1, first0 = tn0 <= tn1;
                 if (both) stack[sp] = first0 ? ch1 : ch0;
                 sp += both ? 1 : 0;
                 const int nxt = (both ? first0 : i0) ? ch0 : ch1;
                 if (i0 || i1) node = nxt;
                 else if (sp) node = stack[--sp];
-                else my = -1;
-#else
-                if (i0 && i1) {
-#if MCS_NEAR_FIRST
-                    const bool first0 = tn0 <= tn1;        // nearer child first
-#else
-                    const bool first0 = true;
-#endif
-                    stack[sp++] = first0 ? ch1 : ch0;
-                    node = first0 ? ch0 : ch1;
-                } else if (i0) node = ch0;
-                else if (i1) node = ch1;
-                else if (sp) node = stack[--sp];
                 else my = -1;                               // walk finished; verdict comes from the occluded bit
-#endif
             }
-            // defer the leaf tests
-            const unsigned mA = __ballot_sync(0xFFFFFFFFu, hasA);
-            if (hasA) { const int e = pend + __popc(mA & lt); pl_ray[e] = (uint16_t)cur; pl_leaf[e] = leafA; }
-            pend += __popc(mA);
-            const unsigned mB = __ballot_sync(0xFFFFFFFFu, hasB);
-            if (hasB) { const int e = pend + __popc(mB & lt); pl_ray[e] = (uint16_t)cur; pl_leaf[e] = leafB; }
-            pend += __popc(mB);
+            // defer the leaf tests: one (ray, leaf run) pair per leaf child hit; a second ballot only when some lane hit two
+            const unsigned mL = __ballot_sync(0xFFFFFFFFu, lmask != 0u);
+            if (lmask) pl[pend + __popc(mL & lt)] = make_uint2((unsigned)cur, (unsigned)((lmask & 1u) ? ch0 : ch1));
+            pend += __popc(mL);
+            const unsigned m2 = __ballot_sync(0xFFFFFFFFu, lmask == 3u);
+            if (m2) {
+                if (lmask == 3u) pl[pend + __popc(m2 & lt)] = make_uint2((unsigned)cur, (unsigned)ch1);
+                pend += __popc(m2);
+            }
+#endif
             nact = __popc(__ballot_sync(0xFFFFFFFFu, my >= 0));
         } while (pend < LEAF_BATCH && nact >= thresh);
         while (pend >= LEAF_BATCH) leaf_batch(32);
-#if MCS_POLL_AFTER_BATCH
         // occluded bits of this warp's rays only change inside leaf_batch (a ray is walked and leaf-tested by one warp):
         // poll here instead of once per node step
         if (my >= 0 && (q.tex[my] >> 31)) my = -1;
-#endif
     }
     __syncwarp();
 }
@@ -961,7 +1014,7 @@ static int fill_params(mcs_ctx *ctx, EnvParams &p,
     p.perms = (const int32_t *)perms->ptr; p.pm_s1 = perms->strides[1]; p.pm_s3 = perms->strides[3]; p.n_perms = (uint32_t)perms->sizes[1];
     p.m_rows = cdf_iters(p.Hl); p.m_cols = cdf_iters(p.Wl);
     p.bsdf = bsdf; p.seed = rnd_seed; p.batch_offset = batch_offset; p.shadow_scale = shadow_scale;
-    p.bvh = BvhView{(const float4 *)ctx->nodes.p, (const float4 *)ctx->tris.p};
+    p.bvh = BvhView{(const float4 *)ctx->nodes.p, (const float4 *)ctx->tris.p, (const uint4 *)ctx->nodesq.p, (const float *)ctx->qgrid.p, (const uint4 *)ctx->nodesq4.p};
     if (int e = ensure_skip_table(ctx, p.N, s)) return e;
     p.skip = (const uint2 *)((const char *)ctx->lcg_skip.p);
     if (int e = mcs_buf_reserve(ctx->light_grad4, 256, s)) return e;
