@@ -506,7 +506,8 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
 {
     constexpr int REFILL_BELOW = MCS_REFILL_BELOW;
     constexpr int LEAF_BATCH = MCS_LEAF_BATCH;
-    const unsigned lt = (1u << lane) - 1u;
+    unsigned lt;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
     int pend = 0;
     int my = -1;
     int node = 0, sp = 0;
@@ -601,9 +602,10 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
             // defer the leaf tests: one (ray, leaf run) pair per leaf child hit, one ballot round per pair of the busiest lane
             for (unsigned mL = __ballot_sync(0xFFFFFFFFu, lmask != 0u); mL; mL = __ballot_sync(0xFFFFFFFFu, lmask != 0u)) {
                 if (lmask) {
-                    const int c = __ffs(lmask) - 1;
-                    pl[pend + __popc(mL & lt)] = make_uint2((unsigned)cur, (unsigned)(c == 0 ? c0 : (c == 1 ? c1 : (c == 2 ? c2 : c3))));
-                    lmask &= lmask - 1u;
+                    const unsigned low = lmask & (0u - lmask);
+                    const int code = (low & 3u) ? ((low & 1u) ? c0 : c1) : ((low & 4u) ? c2 : c3);
+                    pl[pend + __popc(mL & lt)] = make_uint2((unsigned)cur, (unsigned)code);
+                    lmask ^= low;
                 }
                 pend += __popc(mL);
             }
