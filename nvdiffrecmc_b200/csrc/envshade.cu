@@ -437,20 +437,6 @@ __device__ __forceinline__ void gen_segment(const EnvParams &p, BlockQueue &q, B
     }
 }
 
-// ---- phase T: any-hit traversal of all queued rays of the CTA: work stealing + dynamic fetch + deferred leaf tests ----
-// SIMT-friendly organisation (profiles/r01_v2_*: a classic while-while loop ran at 13/32 lanes because lanes wait for each
-// other at every leaf):
-//   * node loop: every busy lane performs exactly one node step per iteration (fetch a 64-byte node holding both children's
-//     boxes, two slab tests, descend / push / pop).  Leaf children that pass the slab test are NOT intersected here: the
-//     (ray, leaf) pair is appended to the warp's pending list (ballot compaction) and the lane keeps walking, speculating
-//     that the leaf misses;
-//   * as soon as 32 pairs are pending the warp intersects them with all lanes busy; a hit sets the ray's "occluded" bit
-//     (tex bit 31), which the owning lane polls once per node step to abandon the walk;
-//   * a lane whose walk ends pulls the next ray -- from the warp's own segment first, then from the other warps' segments --
-//     as soon as fewer than REFILL_BELOW lanes are busy;
-//   * visibility of a ray = its occluded bit after all segments AND all pending lists have drained (block barrier).
-// (An 8-wide compressed BVH, bvh8.cuh, was measured too: it removes the L2 round trips but its unrolled node test is
-//  instruction-fetch bound and ended up 15 % slower; profiles/r01_bvh8_*.)
 // Per-ray constants of the quantised node test (bvh.cu:k_emit_nodesq): plane t = (origin + q * cell - o) / d = q' * A + B with
 // q' = 2^23 + q (the float whose low mantissa bits are the 16-bit coordinate), A = cell / d (exact: cell is a power of two),
 // B = (origin - o) / d - 2^23 * A.  |error| < 0.51 cell (rounding of B), covered by the two-cell inflation of the stored boxes.
@@ -489,8 +475,8 @@ __device__ __forceinline__ bool qslab(const uint4 c, const RayQ &r, float &tn)
 // ---- phase T: any-hit traversal of all queued rays of the CTA: work stealing + dynamic fetch + deferred leaf tests ----
 // SIMT-friendly organisation (profiles/r01_v2_*: a classic while-while loop ran at 13/32 lanes because lanes wait for each
 // other at every leaf):
-//   * node loop: every busy lane performs exactly one node step per iteration (fetch the 32-byte quantised node: one 128-bit
-//     load per child, two slab tests, descend / push / pop).  Leaf children that pass the slab test are NOT intersected here:
+//   * node loop: every busy lane performs exactly one node step per iteration (fetch the quantised node -- 64 bytes, four
+//     children, one 128-bit load per child -- four slab tests, push / continue / pop).  Leaf children that pass the slab test are NOT intersected here:
 //     the (ray, leaf run) pair is appended to the warp's pending list (ballot compaction) and the lane keeps walking,
 //     speculating that the leaf misses;
 //   * as soon as 32 pairs are pending the warp intersects them with all lanes busy; a hit sets the ray's "occluded" bit
@@ -498,10 +484,12 @@ __device__ __forceinline__ bool qslab(const uint4 c, const RayQ &r, float &tn)
 //   * a lane whose walk ends pulls the next ray -- from the warp's own segment first, then from the other warps' segments --
 //     as soon as fewer than REFILL_BELOW lanes are busy;
 //   * visibility of a ray = its occluded bit after all segments AND all pending lists have drained (block barrier).
-// What bounds it (profiles/r01_v6_*): instruction issue.  With fp32 64-byte nodes (4 loads per visit) the L1 data pipe was a
-// co-limiter at 75 %; the quantised nodes took it to 47 % and long-scoreboard stalls from 25 % to 18 %.  A 4-wide fp32 node
-// (half the visits, 7 loads each) and fetching through the texture path were measured and were slower / equal; an 8-wide
-// compressed node (bvh8.cuh) costs more instructions per ray than it saves.
+// What bounds it (profiles/r01_v6_*): instruction issue (73 % of peak, ~22 of 32 lanes).  With fp32 64-byte binary nodes (4 loads
+// per visit) the L1 data pipe was a co-limiter at 75 %; quantised nodes took it to 47 % and long-scoreboard stalls from 25 % to
+// 18 % at equal run time; the 4-wide view then halves the visits (13.8 vs 28.8 per ray) for -8 % run time.  Measured and
+// rejected: 4-wide fp32 nodes (7 loads per visit: L1-bound, +5 %), node fetch through the texture path (equal), per-node
+// instead of per-leaf deferral (leaf phase drops to 17 lanes), an 8-wide compressed node (bvh8.cuh: more instructions per ray),
+// sorting the BSDF samples of a pixel by lobe before sampling (one routine per chunk instead of two at 16 lanes: +1.7 %).
 __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, const int warp, const int lane)
 {
     constexpr int REFILL_BELOW = MCS_REFILL_BELOW;
