@@ -42,42 +42,58 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  nvidia-smi needs a few hundred ms to
+    start, so the poller is started before the warm-up steps and every sample is time-stamped; the summary uses the samples that fall
+    inside the timed window (and says so), falling back to the samples taken under the warm-up load if the window caught < 2."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.index, self.samples, self.stop, self.th, self.proc = index, [], False, None, None
+        self.t_load = self.t0 = self.t1 = None
 
     def _run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 if self.stop:
                     break
                 if line.strip():
-                    self.samples.append([x.strip() for x in line.strip().split(",")])
+                    self.samples.append((time.time(), [x.strip() for x in line.strip().split(",")]))
         except Exception:
             pass
 
-    def __enter__(self):
-        self.th = threading.Thread(target=self._run, daemon=True); self.th.start(); return self
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True); self.th.start(); self.t_load = time.time(); return self
 
-    def __exit__(self, *a):
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
+    def close(self):
         self.stop = True
         try:
             self.proc.terminate()
         except Exception:
             pass
-        self.th.join(timeout=6)
+        if self.th is not None:
+            self.th.join(timeout=6)
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        inside = [s for t, s in self.samples if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e30)]
+        window = "timed region"
+        if len(inside) < 2:
+            inside = [s for t, s in self.samples if t >= (self.t_load or 0) + 0.5 and t <= (self.t1 or 1e30)]
+            window = "warm-up + timed region (timed region shorter than two 50 ms samples)"
+        sm = [float(s[0]) for s in inside if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in inside if len(s) > 1 and s[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({n for s in inside if len(s) >= 6 for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm),
+                "window": window}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -346,7 +362,7 @@ def run_reference(args, wl):
     dt = (time.time() - t0) / args.steps
     val = rays_step / dt / 1e6
     sample = "1 view at %dx%d of the same scene (same mesh, probe, n_samples_x=%d, sigma=%g): %d rays/step" % (res_s, res_s, N, wl["sigma"], rays_step)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "shadow_rays_per_second_train_step", "value": round(val, 4), "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -354,10 +370,30 @@ def run_reference(args, wl):
         "cpu_baseline": {"value": round(val, 4), "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(val, 4), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "iters_per_s_on_sample": round(1.0 / dt, 4),
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------
+_STDOUT_FD = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner when NCCL_DEBUG is set, torchrun
+    notices), so everything but the final line is routed to stderr at the file-descriptor level."""
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(obj))
+    sys.stdout.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -371,6 +407,7 @@ def main():
     ap.add_argument("--level", type=int, default=None, help="override icosphere subdivision level (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    quiet_stdout()
     wl = dict(WORKLOAD)
     if args.views:
         wl["views_per_gpu"] = args.views
@@ -410,6 +447,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput (value) --------------------------------------------------
+    clk = ClockSampler(local).start()
     for _ in range(args.warmup):
         w.step()
     barrier()
@@ -417,13 +455,15 @@ def main():
     timers = [{n: torch.cuda.Event(enable_timing=True) for n in names} for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     _lib.LAUNCHES.clear()
-    with ClockSampler(local) as clk:
-        barrier()
-        e0.record()
-        for i in range(args.steps):
-            w.step(timers[i])
-        e1.record()
-        barrier()
+    barrier()
+    clk.begin()
+    e0.record()
+    for i in range(args.steps):
+        w.step(timers[i])
+    e1.record()
+    barrier()
+    clk.end()
+    clk.close()
     launches = sum(_lib.LAUNCHES.values())
     ms = e0.elapsed_time(e1)
     t_ms = torch.tensor([ms], device=dev)
@@ -563,7 +603,8 @@ def main():
         "roofline": roof,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(out))
+    if rank == 0:
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
