@@ -1,0 +1,92 @@
+"""Developer tool: CUDA-event timings of the secondary kernels against their rooflines: the renderutils streaming ops
+(HBM: algorithmic bytes / time vs MEASURED_PEAKS hbm_gbs), the bilateral denoiser (taps/s), the LBVH build (us, B/tri) and update_pdf.
+usage: python tools/opbench.py [out.json]"""
+import os, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+import bench
+import nvdiffrecmc_b200.renderutils as ru
+import nvdiffrecmc_b200.optixutils as ou
+from nvdiffrecmc_b200 import synth
+from nvdiffrecmc_b200.light import EnvironmentLight
+
+dev = torch.device("cuda:0")
+peak, peak_src = bench.peaks()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+
+def timed(fn, reps=20):
+    fn(); fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+out = {"hbm_peak_gbs": peak, "peak_source": peak_src, "l2_policy": "256 MB buffer rewritten between timed iterations", "ops": []}
+g = torch.Generator().manual_seed(0)
+for shape in [(1, 256, 256), (16, 512, 512), (1, 2048, 2048)]:          # test_bsdf.py RES-like + test_perf.py:54-56 sizes
+    B, H, W = shape
+    npx = B * H * W
+    t = [torch.rand(B, H, W, 3, generator=g).to(dev) for _ in range(7)]
+    kd, arm, pos, nrm, view, light, dout = t
+    ins = [x.clone().requires_grad_(True) for x in (kd, arm, pos, nrm, view, light)]
+    for name, fwd_bytes, bwd_bytes, f in [
+        ("pbr_bsdf", 84, 156, lambda a: ru.pbr_bsdf(a[0], a[1], a[2], a[3], a[4], a[5])),
+        ("prepare_shading_normal", 84, 156, lambda a: ru.prepare_shading_normal(a[2], a[4], a[0], a[3], a[1], a[5], two_sided_shading=True, opengl=True)),
+    ]:
+        with torch.no_grad():
+            ms_f = timed(lambda: f([x.detach() for x in ins]))
+        y = f(ins)
+        ms_b = timed(lambda: torch.autograd.grad(y, ins, dout, retain_graph=True))
+        out["ops"].append({"op": name, "shape": list(shape), "fwd_ms": round(ms_f, 4), "fwd_gbs": round(npx * fwd_bytes / ms_f / 1e6, 1),
+                           "fwd_frac_of_hbm_peak": round(npx * fwd_bytes / ms_f / 1e6 / peak, 3), "bwd_ms": round(ms_b, 4),
+                           "bwd_gbs": round(npx * bwd_bytes / ms_b / 1e6, 1), "bwd_frac_of_hbm_peak": round(npx * bwd_bytes / ms_b / 1e6 / peak, 3),
+                           "algorithmic_bytes_per_px": [fwd_bytes, bwd_bytes]})
+        print(out["ops"][-1], flush=True)
+
+# bilateral denoiser, sigma = 2 (23 x 23 taps), 8 x 512 x 512
+B, H, W = 8, 512, 512
+col = torch.rand(B, H, W, 3, generator=g).to(dev).requires_grad_(True)
+nrm = torch.nn.functional.normalize(torch.rand(B, H, W, 3, generator=g).to(dev) - 0.5, dim=-1)
+zdz = torch.stack([torch.rand(B, H, W, generator=g).to(dev) + 1, torch.full((B, H, W), 0.01, device=dev)], -1)
+with torch.no_grad():
+    ms_f = timed(lambda: ou.bilateral_denoiser(col.detach(), nrm, zdz, 2.0))
+y = ou.bilateral_denoiser(col, nrm, zdz, 2.0)
+gy = torch.rand_like(y)
+ms_b = timed(lambda: torch.autograd.grad(y, col, gy, retain_graph=True))
+taps = B * H * W * 23 * 23
+out["bilateral_denoiser"] = {"shape": [B, H, W], "sigma": 2.0, "taps_per_px": 529, "fwd_ms": round(ms_f, 4), "bwd_ms": round(ms_b, 4),
+                             "fwd_gtaps_per_s": round(taps / ms_f / 1e6, 1), "fwd_gbs_compulsory_48B_per_px": round(B * H * W * 48 / ms_f / 1e6, 1)}
+print(out["bilateral_denoiser"], flush=True)
+
+# LBVH build
+out["bvh_build"] = []
+for kind, level in [("blob+torus", 4), ("grid1m", 0)]:
+    wl = dict(bench.WORKLOAD); wl["mesh"] = kind; wl["mesh_level"] = level
+    v, f, _ = bench.build_scene_numpy(wl, 0)
+    vt, ft = torch.tensor(v, device=dev), torch.tensor(f, device=dev)
+    ctx = ou.OptiXContext()
+    ms = timed(lambda: ou.optix_build_bvh(ctx, vt, ft, rebuild=1))
+    ms_refit = timed(lambda: ou.optix_build_bvh(ctx, vt, ft, rebuild=0))
+    T = int(ft.shape[0])
+    out["bvh_build"].append({"mesh": kind, "triangles": T, "rebuild_ms": round(ms, 4), "refit_ms": round(ms_refit, 4),
+                             "rebuild_gbs_at_248B_per_tri": round(T * 248 / ms / 1e6, 1), "mtris_per_s": round(T / ms / 1e3, 1)})
+    print(out["bvh_build"][-1], flush=True)
+
+# update_pdf
+out["update_pdf"] = []
+for hw in [(256, 256), (1024, 2048)]:
+    lgt = EnvironmentLight(torch.rand(hw[0], hw[1], 3, generator=g).to(dev))
+    ms = timed(lgt.update_pdf)
+    ms_py = timed(lambda: lgt.update_pdf(use_python=True))
+    out["update_pdf"].append({"probe": list(hw), "native_ms": round(ms, 4), "torch_ops_ms": round(ms_py, 4), "native_gbs_at_28B_per_texel": round(hw[0] * hw[1] * 28 / ms / 1e6, 1)})
+    print(out["update_pdf"][-1], flush=True)
+
+if len(sys.argv) > 1:
+    json.dump(out, open(sys.argv[1], "w"), indent=1)
