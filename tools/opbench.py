@@ -14,7 +14,7 @@ from nvdiffrecmc_b200.light import EnvironmentLight
 
 dev = torch.device("cuda:0")
 peak, peak_src = bench.peaks()
-flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+flush = torch.empty(1 << 30, dtype=torch.uint8, device=dev)          # > 126 MB L2; long enough (~0.3 ms) to hide the host-side launch cost of the timed op
 
 
 def timed(fn, reps=20):
@@ -28,7 +28,7 @@ def timed(fn, reps=20):
     return float(np.median(ts))
 
 
-out = {"hbm_peak_gbs": peak, "peak_source": peak_src, "l2_policy": "256 MB buffer rewritten between timed iterations", "ops": []}
+out = {"hbm_peak_gbs": peak, "peak_source": peak_src, "l2_policy": "1 GB buffer rewritten between timed iterations", "ops": []}
 g = torch.Generator().manual_seed(0)
 for shape in [(1, 256, 256), (16, 512, 512), (1, 2048, 2048)]:          # test_bsdf.py RES-like + test_perf.py:54-56 sizes
     B, H, W = shape
@@ -67,7 +67,7 @@ print(out["bilateral_denoiser"], flush=True)
 
 # LBVH build
 out["bvh_build"] = []
-for kind, level in [("blob+torus", 4), ("grid1m", 0)]:
+for kind, level in ([("blob+torus", 4), ("grid1m", 0)] if not os.environ.get("OPB_QUICK") else []):
     wl = dict(bench.WORKLOAD); wl["mesh"] = kind; wl["mesh_level"] = level
     v, f, _ = bench.build_scene_numpy(wl, 0)
     vt, ft = torch.tensor(v, device=dev), torch.tensor(f, device=dev)
