@@ -9,8 +9,9 @@
 //     reads 32 consecutive floats of a plane row);
 //   * each thread produces two vertically adjacent outputs so every tap value read from shared
 //     memory is used twice (halves LDS traffic, the co-limiter next to the FP32/MUFU pipes);
-//   * the spatial gaussian and the tap distance come from a per-CTA table; gaussian and depth term
-//     are merged into ONE exp2 (exp(a)*exp(b) = exp2((a+b)*log2 e)); pow(x,128) is 7 squarings;
+//   * the spatial gaussian exponent is one FMA on a running tap offset; gaussian and depth term are merged into ONE
+//     ex2.approx (exp(a)*exp(b) = exp2((a+b)*log2 e)); 1/max(dz*dist, eps) = min(inv_dz * rsqrt(dist^2), 1/eps) with the
+//     guarded 1/dz staged per pixel; pow(x,128) is 7 squarings -- 2 MUFU and no table look-up per tap;
 //   * out-of-image taps are stored as zero normals => clamp(dot, 1e-4, 1)^128 underflows to exactly
 //     0, which reproduces the reference's `continue` without a branch;
 //   * the diffuse and specular signals, which render.py:120-121 filters with identical guides, can
@@ -33,6 +34,13 @@ struct BilateralParams {
     float neg_inv_2var_log2e;   // -log2(e) / (2 sigma^2)
 };
 
+// MUFU approximations without the range-handling wrappers of exp2f / __fdividef (their operands are bounded here: exponents
+// <= 0, where a flushed denormal weight is indistinguishable from the reference's 1e-38; reciprocal arguments >= 1e-4)
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// 1 / max(dz * dist, 1e-4) = min(inv_dz * rsqrt(dist^2), 1e4) with inv_dz = dz > 0 ? 1/dz : +inf  (dist = 0 -> inf -> 1e4 as well)
+__device__ __forceinline__ float guarded_inv(float dz) { return dz > 0.0f ? 1.0f / dz : INFINITY; }
+
 __device__ __forceinline__ float pow128(float x)
 {
     x *= x; x *= x; x *= x; x *= x; x *= x; x *= x; x *= x;
@@ -48,19 +56,11 @@ __global__ void __launch_bounds__(256) bilateral_kernel(BilateralParams p)
     const int plane = tw * th;
     float *s_nx = smem, *s_ny = s_nx + plane, *s_nz = s_ny + plane, *s_z = s_nz + plane, *s_dz = s_z + plane;
     float *s_sig = s_dz + plane;                       // NSIG * 3 planes
-    float *s_g = s_sig + NSIG * 3 * plane;             // (r+2) x (r+1) : exponent of the spatial gaussian (log2 domain)
-    float *s_d = s_g + (r + 2) * (r + 1);              // (r+2) x (r+1) : tap distance
 
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * TILE_W - r, y0 = blockIdx.y * TILE_H - r;
 
-    for (int i = tid; i < (r + 2) * (r + 1); i += 256) {
-        int fy = i / (r + 1), fx = i % (r + 1);
-        float d2 = (float)(fx * fx + fy * fy);
-        s_g[i] = fy > r ? -INFINITY : d2 * p.neg_inv_2var_log2e;
-        s_d[i] = sqrtf(d2);
-    }
     for (int i = tid; i < plane; i += 256) {
         int ty = i / tw, tx = i - ty * tw;
         int gy = y0 + ty, gx = x0 + tx;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) bilateral_kernel(BilateralParams p)
             const float *q = p.zdz.p + p.zdz.off(b, gy, gx);
             z = __ldg(q); dz = __ldg(q + p.zdz.s3);
         }
-        s_nx[i] = n.x; s_ny[i] = n.y; s_nz[i] = n.z; s_z[i] = z; s_dz[i] = dz;
+        s_nx[i] = n.x; s_ny[i] = n.y; s_nz[i] = n.z; s_z[i] = z; s_dz[i] = guarded_inv(dz);     // plane holds 1/dz (guarded)
 #pragma unroll
         for (int s = 0; s < NSIG; ++s) {
             f3 c = F3(0.0f);
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) bilateral_kernel(BilateralParams p)
 #pragma unroll
     for (int o = 0; o < 2; ++o) {
         int ci = (lyA + o + r) * tw + cxs;
-        cn[o] = F3(s_nx[ci], s_ny[ci], s_nz[ci]); cz[o] = s_z[ci]; cdz[o] = s_dz[ci];
+        cn[o] = F3(s_nx[ci], s_ny[ci], s_nz[ci]); cz[o] = s_z[ci]; cdz[o] = s_dz[ci];      // cdz = guarded 1/dz of the centre
     }
     float acc[2][NSIG][3]; float accw[2] = {0.0f, 0.0f};
 #pragma unroll
@@ -96,17 +96,21 @@ __global__ void __launch_bounds__(256) bilateral_kernel(BilateralParams p)
 #pragma unroll
         for (int s = 0; s < NSIG; ++s) acc[o][s][0] = acc[o][s][1] = acc[o][s][2] = 0.0f;
 
+    const float k2 = p.neg_inv_2var_log2e;
     for (int rr = 0; rr <= 2 * r + 1; ++rr) {
-        const int fyA = rr - r;                 // tap offset for output A; output B sees fyA - 1
-        const int afy0 = abs(fyA), afy1 = abs(fyA - 1);
-        const float *row_nx = s_nx + (lyA + rr) * tw + lx;
+        // tap row rr of the tile serves output A at vertical offset rr - r and output B at rr - r - 1; a row outside an output's
+        // window gets exponent -inf (weight exactly 0)
+        const float fyA = (float)(rr - r), fyB = (float)(rr - r - 1);
+        const float fy2[2] = {fyA * fyA, fyB * fyB};
+        const float gy[2] = {rr <= 2 * r ? fy2[0] * k2 : -INFINITY, rr >= 1 ? fy2[1] * k2 : -INFINITY};
         const int rowoff = (lyA + rr) * tw + lx;
-        for (int cx = 0; cx <= 2 * r; ++cx) {
-            const int afx = abs(cx - r);
+        float fx = (float)(-r);
+        for (int cx = 0; cx <= 2 * r; ++cx, fx += 1.0f) {
             const int i = rowoff + cx;
-            f3 tn = F3(row_nx[cx], s_ny[i], s_nz[i]);
+            const float fx2 = fx * fx;
+            f3 tn = F3(s_nx[i], s_ny[i], s_nz[i]);
             float tz = s_z[i];
-            float tdz = BWD ? s_dz[i] : 0.0f;
+            float tinv = BWD ? s_dz[i] : 0.0f;
             float sg[NSIG][3];
 #pragma unroll
             for (int s = 0; s < NSIG; ++s) {
@@ -114,13 +118,11 @@ __global__ void __launch_bounds__(256) bilateral_kernel(BilateralParams p)
             }
 #pragma unroll
             for (int o = 0; o < 2; ++o) {
-                const int li = (o == 0 ? afy0 : afy1) * (r + 1) + afx;
-                float g = s_g[li], dist = s_d[li];
                 float wn = pow128(fminf(fmaxf(dot(tn, cn[o]), FLT_EPS_), 1.0f));
                 // fwd: centre's dz (denoising.cu:59); bwd: tap's dz (denoising.cu:118)
-                float den = fmaxf((BWD ? tdz : cdz[o]) * dist, FLT_EPS_);
-                float e = g - LOG2E * __fdividef(fabsf(tz - cz[o]), den);
-                float w = wn * exp2f(e);
+                const float inv_den = fminf((BWD ? tinv : cdz[o]) * rsqrt_approx(fx2 + fy2[o]), 1.0f / FLT_EPS_);
+                const float e = fmaf(fx2, k2, gy[o]) - LOG2E * (fabsf(tz - cz[o]) * inv_den);
+                float w = wn * ex2_approx(e);
 #pragma unroll
                 for (int s = 0; s < NSIG; ++s) {
                     acc[o][s][0] = fmaf(sg[s][0], w, acc[o][s][0]);
@@ -169,7 +171,7 @@ static int launch_bilateral(BilateralParams &p, float sigma, cudaStream_t stream
     p.r = 2 * (int)ceilf(sigma * 2.5f) + 1;                 // denoising.cu:28 filter_rad
     p.neg_inv_2var_log2e = -LOG2E / (2.0f * sigma * sigma);
     int tw = TILE_W + 2 * p.r, th = TILE_H + 2 * p.r;
-    size_t smem = sizeof(float) * ((size_t)(5 + 3 * NSIG) * tw * th + 2 * (size_t)(p.r + 2) * (p.r + 1));
+    size_t smem = sizeof(float) * ((size_t)(5 + 3 * NSIG) * tw * th);
     MCS_REQUIRE(smem <= 227 * 1024, "bilateral: sigma %.3f needs a %zu-byte tile (> 227 KB shared memory)", sigma, smem);
     auto kern = bilateral_kernel<NSIG, BWD>;
     MCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
