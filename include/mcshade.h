@@ -190,6 +190,18 @@ int mcs_image_loss_bwd(const mcs_tensor *img, const mcs_tensor *target, int32_t 
 int mcs_xfm_fwd(const mcs_tensor *points, const mcs_tensor *matrix, int32_t is_points, float *out, mcs_stream s);
 int mcs_xfm_bwd(const mcs_tensor *points, const mcs_tensor *matrix, const mcs_tensor *d_out, int32_t is_points, float *d_points, mcs_stream s);
 
+/* ---- primary visibility + attribute interpolation: stands in for dr.rasterize / dr.interpolate of nvdiffrast at
+ *      the call sites render/render.py:208-234 (closest hit on the context's LBVH instead of rasterisation).
+ *      mtx: [B,4,4] row-major fp32 device array, clip = mtx * (p, 1) (inverted on the device, no host round trip).  rast: [B,H,W,4] contiguous, nvdiffrast
+ *      convention (u, v, z/w, triangle_id + 1) with u / v the barycentric weights of vertex 0 / 1; all zero = background.
+ *      interpolate: attr [V,C] (attr_batch_stride 0) or [B,V,C] (stride V*C), tris int32 [T,3], out / d_out [B,H,W,C];
+ *      d_attr (same layout as attr) must be zeroed by the caller and receives float atomics. */
+int mcs_rasterize(mcs_ctx *ctx, const float *mtx, int32_t B, int32_t H, int32_t W, float *rast, mcs_stream stream);
+int mcs_interpolate_fwd(const float *attr, int64_t attr_batch_stride, int32_t V, int32_t C, const int32_t *tris, int32_t T, const float *rast,
+                        int32_t B, int32_t H, int32_t W, float *out, mcs_stream stream);
+int mcs_interpolate_bwd(const float *attr, int64_t attr_batch_stride, int32_t V, int32_t C, const int32_t *tris, int32_t T, const float *rast,
+                        int32_t B, int32_t H, int32_t W, const float *d_out, float *d_attr, mcs_stream stream);
+
 /* ---- env-light pdf / CDF tables: replaces the torch-op chain of EnvironmentLight.update_pdf,
  *      render/light.py:46-59.  base: (1, Hl, Wl, 3) view.  Outputs (caller-allocated, contiguous): pdf [Hl,Wl] normalised to sum 1,
  *      rows [Hl] (what the call site passes as lgt.rows[:,0], render/render.py:114), cols [Hl,Wl]; row_totals: Hl doubles of scratch

@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 _LIBDIR = os.path.join(_PKG, "lib")
 LIB_PATH = os.environ.get("MCS_LIB", os.path.join(_LIBDIR, "libmcshade.so"))     # MCS_LIB: developer override (kernel variants)
-SOURCES = ["core.cu", "elementwise.cu", "denoise.cu", "bvh.cu", "envshade.cu", "lossmesh.cu", "light.cu"]
+SOURCES = ["core.cu", "elementwise.cu", "denoise.cu", "bvh.cu", "envshade.cu", "lossmesh.cu", "light.cu", "raster.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 
 
@@ -109,6 +109,9 @@ _SIGS = {
     "mcs_xfm_fwd": ([_T, _T, C.c_int32, _P, _P], C.c_int),
     "mcs_xfm_bwd": ([_T, _T, _T, C.c_int32, _P, _P], C.c_int),
     "mcs_update_pdf": ([_T, _P, _P, _P, _P, _P], C.c_int),
+    "mcs_rasterize": ([_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P], C.c_int),
+    "mcs_interpolate_fwd": ([_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P], C.c_int),
+    "mcs_interpolate_bwd": ([_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P], C.c_int),
 }
 EXPORTED_SYMBOLS = sorted(_SIGS)
 
@@ -133,10 +136,11 @@ def lib():
     return l
 
 
-# Count of OUR kernels launched through the C ABI (bench.py's gpu_launches claim).  optix_build_bvh launches six hand-written
-# kernels (bounds init, triangle bounds, Morton codes, Karras topology, leaves + refit, node emission) around one CUB radix sort.
+# Count of OUR kernels launched through the C ABI (bench.py's gpu_launches claim).  optix_build_bvh launches seven hand-written
+# kernels (bounds init, triangle bounds, Morton codes, Karras topology, leaves + refit, fp32 node emission, quantised node emission)
+# around one CUB radix sort.
 LAUNCHES = collections.Counter()
-_KERNELS_PER_CALL = {"optix_build_bvh": 6, "bvh_export": 0, "update_pdf": 2}
+_KERNELS_PER_CALL = {"optix_build_bvh": 7, "bvh_export": 0, "update_pdf": 2, "rasterize": 2}
 
 
 def check(status, what):

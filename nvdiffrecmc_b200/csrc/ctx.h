@@ -38,6 +38,7 @@ struct mcs_ctx {
     DevBuf lcg_skip;             // [5*N*N+3] x uint2 (mul, add) LCG jump-ahead table for n_samples_x = skip_N
     int skip_N = 0;
     DevBuf light_grad4;          // scratch
+    DevBuf mtx_inv;              // [B,4,4] inverse clip matrices of the last mcs_rasterize call
 };
 
 int mcs_buf_reserve(DevBuf &b, size_t bytes, cudaStream_t s);
