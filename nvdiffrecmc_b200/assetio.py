@@ -2,7 +2,9 @@
 
   * Radiance RGBE `.hdr` reader / writer  -- the reference goes through imageio (render/util.py:355-384; light.py:71-79 load_env,
     light.py:89-93 save_env_map);
-  * Wavefront `.obj` reader / writer (positions, normals, texcoords, triangulated faces) -- render/obj.py:31-176.
+  * Wavefront `.obj` reader / writer (positions, normals, texcoords, triangulated faces) -- render/obj.py:31-176;
+  * Wavefront `.mtl` reader / writer (statement level) -- render/material.py:21-95;
+  * PNG reader / writer (8 / 16 bit, grey / grey+alpha / RGB / RGBA, all five scanline filters) -- texture maps, render/util.py:355-376.
 
 numpy only; tensors are created by the caller.  The HDR reader handles flat and new-style run-length-encoded scanlines, the writer
 emits flat scanlines (every reader accepts them).
@@ -160,3 +162,155 @@ def save_obj(path, v_pos, t_pos_idx, v_nrm=None, t_nrm_idx=None, v_tex=None, t_t
                     s += "/" + str(int(t_nrm_idx[i][c]) + 1)
                 toks.append(s)
             f.write("f " + " ".join(toks) + "\n")
+
+
+# ------------------------------------------------------------------------------------------------ Wavefront MTL
+_MTL_PATHS = ("bsdf", "map_kd", "map_ks", "bump", "map_bump", "map_d", "map_ka", "map_ke")
+
+
+def load_mtl(path):
+    """-> list of dicts, one per `newmtl` block, keys lower-cased: 'name', path-valued statements (`bsdf`, `map_kd`, `map_ks`, `bump`,
+    kept as strings relative to the .mtl) and numeric statements (`kd`, `ks`, `ka`, `ns`, ...) as float32 arrays.  'bsdf' defaults to
+    'pbr' (render/material.py:21-48; the conversion of constants / image maps into mip-mapped textures, :50-69, stays with the caller)."""
+    materials = []
+    with open(path, "r") as f:
+        for raw in f:
+            line = raw.split("#", 1)[0].split()
+            if not line:
+                continue
+            key, data = line[0].lower(), line[1:]
+            if key == "newmtl":
+                materials.append({"name": data[0] if data else ""})
+            elif materials and data:
+                m = materials[-1]
+                if key in _MTL_PATHS:
+                    m[key] = data[-1]                       # options such as `-bm 1.0` precede the file name
+                else:
+                    try:
+                        m[key] = np.asarray([float(d) for d in data], np.float32)
+                    except ValueError:
+                        m[key] = " ".join(data)
+    for m in materials:
+        m.setdefault("bsdf", "pbr")
+    return materials
+
+
+def save_mtl(path, materials):
+    """Inverse of load_mtl for the statements render/material.py:75-95 writes (name, bsdf, map_* / bump paths, numeric constants)."""
+    with open(path, "w") as f:
+        for m in materials:
+            f.write("newmtl %s\n" % m.get("name", "defaultMat"))
+            for k, v in m.items():
+                if k == "name":
+                    continue
+                if isinstance(v, str):
+                    f.write("%s %s\n" % (k if k in _MTL_PATHS else k, v))
+                else:
+                    f.write("%s %s\n" % (k, " ".join("%.9g" % float(x) for x in np.ravel(v))))
+            f.write("\n")
+
+
+# ------------------------------------------------------------------------------------------------ PNG (zlib only)
+_PNG_SIG = b"\x89PNG\r\n\x1a\n"
+_PNG_CHANNELS = {0: 1, 2: 3, 4: 2, 6: 4}
+
+
+def _paeth(a, b, c):
+    p = a.astype(np.int32) + b - c
+    pa, pb, pc = np.abs(p - a), np.abs(p - b), np.abs(p - c)
+    return np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, b, c)).astype(np.uint8)
+
+
+def load_png(path):
+    """-> uint8 or uint16 array [H, W] / [H, W, C] (grey, grey+alpha, RGB, RGBA; 8 or 16 bit; non-interlaced).  The reference reads
+    texture maps through imageio (render/util.py:355-367: `load_image_raw`); callers divide by 255 / 65535 as it does."""
+    import struct, zlib
+    with open(path, "rb") as f:
+        data = f.read()
+    if data[:8] != _PNG_SIG:
+        raise ValueError("%s: not a PNG file" % path)
+    pos, idat, hdr = 8, [], None
+    while pos < len(data):
+        n, typ = struct.unpack(">I4s", data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        if zlib.crc32(typ + body) & 0xFFFFFFFF != struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0]:
+            raise ValueError("%s: corrupt %s chunk" % (path, typ.decode("latin1")))
+        if typ == b"IHDR":
+            hdr = struct.unpack(">IIBBBBB", body)
+        elif typ == b"IDAT":
+            idat.append(body)
+        elif typ == b"IEND":
+            break
+        pos += 12 + n
+    if hdr is None:
+        raise ValueError("%s: missing IHDR" % path)
+    W, H, depth, ctype, comp, filt, interlace = hdr
+    if ctype not in _PNG_CHANNELS or depth not in (8, 16) or interlace != 0:
+        raise ValueError("%s: unsupported PNG variant (colour type %d, depth %d, interlace %d)" % (path, ctype, depth, interlace))
+    C = _PNG_CHANNELS[ctype]
+    bpp = C * depth // 8
+    raw = np.frombuffer(zlib.decompress(b"".join(idat)), np.uint8)
+    stride = W * bpp
+    if raw.size != H * (stride + 1):
+        raise ValueError("%s: truncated image data" % path)
+    rows = raw.reshape(H, stride + 1)
+    out = np.zeros((H, stride), np.uint8)
+    prev = np.zeros(stride, np.uint8)
+    for y in range(H):
+        ft, line = int(rows[y, 0]), rows[y, 1:]
+        if ft == 0:
+            cur = line.copy()
+        elif ft == 2:
+            cur = line + prev
+        elif ft in (1, 3, 4):
+            # left-dependent filters: sequential over pixels, vectorised over the bytes of a pixel
+            cur = np.zeros(stride, np.uint8)
+            lp = line.reshape(W, bpp); pp = prev.reshape(W, bpp); cp = cur.reshape(W, bpp)
+            left = np.zeros(bpp, np.uint8); upleft = np.zeros(bpp, np.uint8)
+            for x in range(W):
+                if ft == 1:
+                    pred = left
+                elif ft == 3:
+                    pred = ((left.astype(np.int32) + pp[x]) >> 1).astype(np.uint8)
+                else:
+                    pred = _paeth(left, pp[x], upleft)
+                cp[x] = lp[x] + pred
+                left, upleft = cp[x], pp[x]
+        else:
+            raise ValueError("%s: bad filter type %d" % (path, ft))
+        out[y] = cur
+        prev = cur
+    if depth == 16:
+        img = out.reshape(H, W, C, 2)
+        img = (img[..., 0].astype(np.uint16) << 8) | img[..., 1]
+    else:
+        img = out.reshape(H, W, C)
+    return img[..., 0] if C == 1 else img
+
+
+def save_png(path, img):
+    """uint8 / uint16 [H,W] or [H,W,{1,2,3,4}] -> PNG (filter 0, zlib level 6).  Floats are taken as [0,1] and written as 8 bit
+    (render/util.py:369-376 `save_image`: clip, *255, round)."""
+    import struct, zlib
+    a = np.asarray(img)
+    if a.dtype.kind == "f":
+        a = np.clip(np.rint(a * 255.0), 0, 255).astype(np.uint8)
+    if a.ndim == 2:
+        a = a[..., None]
+    H, W, C = a.shape
+    ctype = {1: 0, 2: 4, 3: 2, 4: 6}[C]
+    if a.dtype == np.uint16:
+        depth = 16
+        b = np.stack([(a >> 8).astype(np.uint8), (a & 255).astype(np.uint8)], -1).reshape(H, W * C * 2)
+    elif a.dtype == np.uint8:
+        depth = 8
+        b = a.reshape(H, W * C)
+    else:
+        raise TypeError("save_png: unsupported dtype %s" % a.dtype)
+    raw = np.concatenate([np.zeros((H, 1), np.uint8), b], 1).tobytes()
+
+    def chunk(typ, body):
+        return struct.pack(">I", len(body)) + typ + body + struct.pack(">I", zlib.crc32(typ + body) & 0xFFFFFFFF)
+
+    with open(path, "wb") as f:
+        f.write(_PNG_SIG + chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, depth, ctype, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
