@@ -193,3 +193,22 @@ def test_decorrelated_mode_and_multi_fill_pixels(dev):
     d2, s2 = ou.optix_env_shade(ctx, mask, ro, pos, nrm, view, kd, ks, light, pdf, rows, cols, n_samples_x=N, rnd_seed=None, perms=perms)
     (d2.sum() + s2.sum()).backward()
     assert torch.isfinite(d2).all() and torch.isfinite(light.grad).all()
+
+
+def test_records_on_a_large_mesh(dev):
+    """344 k triangles: leaf boxes are ~100x smaller relative to the scene than in the other cases, which is where the 16-bit
+    quantised nodes lose the most precision.  Visibility must stay bit-exact (conservative culling), radiance within tolerance."""
+    from nvdiffrecmc_b200.optixutils.ops import env_shade_records
+    N = 4
+    c = make_case(res=20, B=1, N=N, level=7, seed=1)
+    assert c["tris"].shape[0] > 300000
+    ctx = _ctx(c, dev)
+    a = _args(c, dev)
+    diff, spec, rec_t, rec_v = env_shade_records(ctx, *a, _t(c, "perms", dev), BSDF="pbr", n_samples_x=N, rnd_seed=5, shadow_scale=1.0)
+    d_ref, s_ref, (rt, rv) = oracle().env_shade(c["scene"], c["mask"], c["ro"], c["pos"], c["nrm"], c["view"], c["kd"], c["ks"], c["light"], c["pdf"],
+                                                c["rows"], c["cols"], c["perms"], BSDF="pbr", n_samples_x=N, rnd_seed=5, records=True, vis_mode="bvh")
+    rec_t, rec_v = rec_t.cpu().numpy(), rec_v.cpu().numpy()
+    assert np.array_equal(rec_t, rt)
+    traced = rec_v != 2
+    assert np.array_equal(rec_v[traced], rv[traced]) and (rv[traced] == 0).sum() > 100
+    assert rel_l2(diff.cpu().numpy(), d_ref) < TOL and rel_l2(spec.cpu().numpy(), s_ref) < TOL
