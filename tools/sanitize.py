@@ -25,5 +25,17 @@ for N in (4, 9):
     ou.optix_build_bvh(ctx, t("verts"), t("tris"), 0)
     v = ou.trace_visibility(ctx, t("ro").reshape(-1, 3), torch.nn.functional.normalize(torch.randn(c["ro"].size // 3, 3, device=dev), dim=-1))
     pts = ru.xfm_points(t("verts")[None], torch.rand(2, 4, 4, device=dev))
+    # re-tracing backward (decorrelated seeds), update_pdf, rasterize / interpolate
+    d2, s2 = ou.optix_env_shade(ctx, t("mask"), t("ro"), pos, nrm.detach().requires_grad_(True), t("view"), kd, ks, light, t("pdf"), t("rows"), t("cols"), n_samples_x=N, rnd_seed=None,
+                                perms=t("perms"))
+    (d2.sum() + s2.sum()).backward()
+    from nvdiffrecmc_b200.light import EnvironmentLight
+    from nvdiffrecmc_b200.raster import rasterize, interpolate
+    lg = EnvironmentLight(light.detach())
+    proj = torch.tensor([[2.4, 0, 0, 0], [0, -2.4, 0, 0], [0, 0, -1.02, -0.2], [0, 0, -1, 0]], device=dev)
+    mv = torch.eye(4, device=dev); mv[2, 3] = -3.0
+    rast = rasterize(ctx, (proj @ mv)[None], (24, 24))
+    att = t("verts").clone().requires_grad_(True)
+    interpolate(att, rast, t("tris"))[0].sum().backward()
 torch.cuda.synchronize()
 print("sanitize workload ok", float(loss), int(v.sum()), tuple(pts.shape))
