@@ -15,13 +15,11 @@
 //   4. karras      : Karras-2012 topology, one thread per internal node
 //   5. leaves+refit: padded leaf boxes, sorted triangle records (v0,e1,e2 as 3 x float4), bottom-up
 //                    box union with arrival counters (second thread to arrive continues)
-//   6. emit        : 64-byte binary traversal nodes (closest-hit queries) holding both children's boxes
-//   7. build_wide  : (MCS_BVH8=1 only) collapse into the 8-wide compressed layout of bvh8.cuh -- a measured experiment, not the default
+//   6. emit        : 64-byte fp32 binary traversal nodes holding both children's boxes (stand-alone visibility / closest-hit queries)
+//   7. emit_nodesq : 16-bit quantised child records on a scene-wide power-of-two grid, as a binary (2 x 16 B) and a 4-wide
+//                    (4 x 16 B, the grandchildren) view of the same tree -- what the fused kernel's shadow rays walk
 #include <cub/cub.cuh>
-#ifndef MCS_BVH8
-#define MCS_BVH8 0      // 1: also build the 8-wide compressed layout (bvh8.cuh) and use it for mcs_trace_visibility (experiment)
-#endif
-#include "bvh8.cuh"
+#include "bvh_traverse.cuh"
 #include "ctx.h"
 
 int mcs_buf_reserve(DevBuf &b, size_t bytes, cudaStream_t s)
@@ -314,136 +312,13 @@ __global__ void __launch_bounds__(256) k_emit_nodesq(int T, const int32_t *__res
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Collapse of the binary LBVH into the 8-wide compressed layout (bvh8.cuh).  Top-down, level by level inside ONE CTA
-// (the number of wide nodes is ~T/4.5; at 7k triangles this is ~2 us per level, at 1M triangles ~0.3 ms in total):
-// each wide node starts from the two children of its binary node and repeatedly opens the member with the largest
-// surface area until it has 8 members or only leaf runs (<= 3 triangles, consecutive in Morton order) remain.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float box_area(const float *lo, const float *hi, int n)
-{
-    const float dx = hi[3 * (size_t)n] - lo[3 * (size_t)n], dy = hi[3 * (size_t)n + 1] - lo[3 * (size_t)n + 1], dz = hi[3 * (size_t)n + 2] - lo[3 * (size_t)n + 2];
-    return dx * dy + dy * dz + dz * dx;
-}
-__device__ __forceinline__ int2 node_range(int m, int T, const int2 *__restrict__ range)
-{
-    return m >= T - 1 ? make_int2(m - (T - 1), m - (T - 1)) : range[m];
-}
-
-__global__ void __launch_bounds__(1024) k_build_wide(int T, const int32_t *__restrict__ left, const int32_t *__restrict__ right, const int2 *__restrict__ range,
-                                                     const float *__restrict__ lo, const float *__restrict__ hi, const float4 *__restrict__ tris,
-                                                     float4 *__restrict__ nodes8, float4 *__restrict__ tris8, int *wide_bin)
-{
-    __shared__ int s_begin, s_end, s_nwide, s_ntri;
-    const int tid = threadIdx.x;
-    if (tid == 0) { wide_bin[0] = 0; s_begin = 0; s_end = 1; s_nwide = 1; s_ntri = 0; }     // binary node 0 = root (for T == 1 it is the only leaf)
-    __syncthreads();
-    while (s_begin < s_end) {
-        const int begin = s_begin, end = s_end;
-        for (int w = begin + tid; w < end; w += blockDim.x) {
-            const int bnode = wide_bin[w];
-            int mem[8];
-            int n;
-            {
-                const int2 rr = node_range(bnode, T, range);
-                if (rr.y - rr.x + 1 <= 3) { mem[0] = bnode; n = 1; }            // tiny mesh: the root itself is one leaf run
-                else {
-                    mem[0] = left[bnode]; mem[1] = right[bnode]; n = 2;
-                    while (n < 8) {
-                        int best = -1; float ba = -1.0f;
-                        for (int j = 0; j < n; ++j) {
-                            const int2 rj = node_range(mem[j], T, range);
-                            if (rj.y - rj.x + 1 > 3) {
-                                const float a = box_area(lo, hi, mem[j]);
-                                if (a > ba) { ba = a; best = j; }
-                            }
-                        }
-                        if (best < 0) break;
-                        const int m = mem[best];
-                        mem[best] = left[m]; mem[n++] = right[m];
-                    }
-                }
-            }
-            // classify the members
-            int n_int = 0, n_tri = 0;
-            for (int j = 0; j < n; ++j) {
-                const int2 rj = node_range(mem[j], T, range);
-                const int c = rj.y - rj.x + 1;
-                if (c > 3) ++n_int; else n_tri += c;
-            }
-            const int cbase = n_int ? atomicAdd(&s_nwide, n_int) : 0;
-            const int tbase = n_tri ? atomicAdd(&s_ntri, n_tri) : 0;
-            // per-node quantisation grid
-            const float *nlo = lo + 3 * (size_t)bnode, *nhi = hi + 3 * (size_t)bnode;
-            uint32_t eb[3]; float inv[3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const float cell = (nhi[a] - nlo[a]) / 255.0f;
-                uint32_t bits = __float_as_uint(cell);
-                uint32_t ex = (bits >> 23) & 0xFFu;
-                if (bits & 0x7FFFFFu) ++ex;                    // round the cell size up to a power of two
-                ex = min(max(ex, 1u), 253u);
-                eb[a] = ex;
-                inv[a] = __uint_as_float((254u - ex) << 23);   // 1 / 2^(ex-127)
-            }
-            uint32_t imask = 0, meta[2] = {0, 0}, q[6][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};
-            int k_int = 0, toff = 0;
-            for (int j = 0; j < n; ++j) {
-                const int m = mem[j];
-                const int2 rj = node_range(m, T, range);
-                const int c = rj.y - rj.x + 1;
-                uint32_t mb;
-                if (c > 3) {
-                    imask |= 1u << j;
-                    mb = (1u << 5) | (24u + j);
-                    wide_bin[cbase + k_int] = m;
-                    ++k_int;
-                } else {
-                    mb = (((1u << c) - 1u) << 5) | (uint32_t)toff;
-                    for (int t = 0; t < c; ++t) {
-                        const size_t src = 3 * (size_t)(rj.x + t), dst = 3 * (size_t)(tbase + toff + t);
-                        tris8[dst] = tris[src]; tris8[dst + 1] = tris[src + 1]; tris8[dst + 2] = tris[src + 2];
-                    }
-                    toff += c;
-                }
-                meta[j >> 2] |= mb << (8 * (j & 3));
-                const float *clo = lo + 3 * (size_t)m, *chi = hi + 3 * (size_t)m;
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const int ql = min(max((int)floorf((clo[a] - nlo[a]) * inv[a]), 0), 255);
-                    const int qh = min(max((int)ceilf((chi[a] - nlo[a]) * inv[a]), 0), 255);
-                    q[a][j >> 2] |= (uint32_t)ql << (8 * (j & 3));
-                    q[3 + a][j >> 2] |= (uint32_t)qh << (8 * (j & 3));
-                }
-            }
-            float4 *o = nodes8 + 5 * (size_t)w;
-            o[0] = make_float4(nlo[0], nlo[1], nlo[2], __uint_as_float(eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24)));
-            o[1] = make_float4(__uint_as_float((uint32_t)cbase), __uint_as_float((uint32_t)tbase), __uint_as_float(meta[0]), __uint_as_float(meta[1]));
-            o[2] = make_float4(__uint_as_float(q[0][0]), __uint_as_float(q[0][1]), __uint_as_float(q[1][0]), __uint_as_float(q[1][1]));
-            o[3] = make_float4(__uint_as_float(q[2][0]), __uint_as_float(q[2][1]), __uint_as_float(q[3][0]), __uint_as_float(q[3][1]));
-            o[4] = make_float4(__uint_as_float(q[4][0]), __uint_as_float(q[4][1]), __uint_as_float(q[5][0]), __uint_as_float(q[5][1]));
-        }
-        __syncthreads();
-        if (tid == 0) { s_begin = end; s_end = s_nwide; }
-        __syncthreads();
-    }
-}
-
-#if MCS_BVH8
-typedef Bvh8View VisView;
-#else
 typedef BvhView VisView;
-#endif
 __global__ void __launch_bounds__(128) k_visibility(VisView b, const float *__restrict__ ro, const float *__restrict__ rd, int64_t n, uint8_t *__restrict__ vis)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     f3 o = F3(ro[3 * i], ro[3 * i + 1], ro[3 * i + 2]), d = F3(rd[3 * i], rd[3 * i + 1], rd[3 * i + 2]);
-#if MCS_BVH8
-    vis[i] = bvh8_occluded(b, o, d) ? 0 : 1;
-#else
-    vis[i] = bvh_occluded(b, o, d) ? 0 : 1;        // same nodes, triangles and predicate as the fused env_shade kernel
-#endif
+    vis[i] = bvh_occluded(b, o, d) ? 0 : 1;        // fp32 nodes, same triangles and predicate as the fused env_shade kernel
 }
 
 __global__ void __launch_bounds__(128) k_closest(BvhView b, const float *__restrict__ ro, const float *__restrict__ rd, int64_t n,
@@ -478,7 +353,7 @@ int mcs_ctx_destroy(mcs_ctx *c)
 {
     if (!c) return 0;
     DevBuf *bufs[] = {&c->bounds, &c->tlo, &c->thi, &c->keys, &c->keys_alt, &c->vals, &c->vals_alt, &c->left, &c->right, &c->parent,
-                      &c->lo, &c->hi, &c->flags, &c->range, &c->sort_tmp, &c->nodes, &c->tris, &c->nodesq, &c->nodesq4, &c->qgrid, &c->nodes8, &c->tris8, &c->wide_bin, &c->lcg_skip, &c->light_grad4, &c->mtx_inv};
+                      &c->lo, &c->hi, &c->flags, &c->range, &c->sort_tmp, &c->nodes, &c->tris, &c->nodesq, &c->nodesq4, &c->qgrid, &c->lcg_skip, &c->light_grad4, &c->mtx_inv};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     delete c;
@@ -513,11 +388,6 @@ int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris
     if (int e = mcs_buf_reserve(c->nodesq, nT * 2 * sizeof(uint4), s)) return e;
     if (int e = mcs_buf_reserve(c->nodesq4, nT * 4 * sizeof(uint4), s)) return e;
     if (int e = mcs_buf_reserve(c->qgrid, 8 * sizeof(float), s)) return e;
-#if MCS_BVH8
-    if (int e = mcs_buf_reserve(c->nodes8, nT * 5 * sizeof(float4), s)) return e;
-    if (int e = mcs_buf_reserve(c->tris8, nT * 3 * sizeof(float4), s)) return e;
-    if (int e = mcs_buf_reserve(c->wide_bin, nT * sizeof(int), s)) return e;
-#endif
 
     uint32_t *bounds = (uint32_t *)c->bounds.p;
     float *tlo = (float *)c->tlo.p, *thi = (float *)c->thi.p;
@@ -550,11 +420,6 @@ int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris
     k_emit_nodesq<<<nblk(T > 1 ? T - 1 : 1, 256), 256, 0, s>>>(T, (const int32_t *)c->left.p, (const int32_t *)c->right.p, (const int2 *)c->range.p,
                                                                (const float *)c->lo.p, (const float *)c->hi.p, (uint4 *)c->nodesq.p, (uint4 *)c->nodesq4.p, (float *)c->qgrid.p);
     MCS_LAUNCH_CHECK();
-#if MCS_BVH8
-    k_build_wide<<<1, 1024, 0, s>>>(T, (const int32_t *)c->left.p, (const int32_t *)c->right.p, (const int2 *)c->range.p, (const float *)c->lo.p,
-                                    (const float *)c->hi.p, (const float4 *)c->tris.p, (float4 *)c->nodes8.p, (float4 *)c->tris8.p, (int *)c->wide_bin.p);
-    MCS_LAUNCH_CHECK();
-#endif
     c->T = T; c->V = V;
     return 0;
 }
@@ -580,11 +445,7 @@ int mcs_trace_visibility(mcs_ctx *c, const float *ro, const float *rd, int64_t n
     MCS_REQUIRE(c && c->T > 0, "mcs_trace_visibility: no acceleration structure built (call mcs_bvh_build first)");
     MCS_REQUIRE(n >= 0 && (n == 0 || (ro && rd && vis)), "mcs_trace_visibility: bad arguments");
     if (n == 0) return 0;
-#if MCS_BVH8
-    VisView b{(const float4 *)c->nodes8.p, (const float4 *)c->tris8.p};
-#else
     VisView b{(const float4 *)c->nodes.p, (const float4 *)c->tris.p, nullptr, nullptr, nullptr};
-#endif
     k_visibility<<<nblk(n, 128), 128, 0, (cudaStream_t)stream>>>(b, ro, rd, n, vis);
     MCS_LAUNCH_CHECK();
     return 0;

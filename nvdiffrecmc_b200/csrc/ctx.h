@@ -30,10 +30,6 @@ struct mcs_ctx {
     DevBuf nodesq;               // [max(T-1,1)] x 2 uint4: the same nodes with 16-bit boxes on a global power-of-two grid (shadow rays)
     DevBuf nodesq4;              // [max(T-1,1)] x 4 uint4: 4-wide view (the <= 4 grandchildren of binary node i), same child records
     DevBuf qgrid;                // 6 floats: grid origin xyz, cell size xyz
-    // ---- 8-wide compressed layout used by the shadow rays (bvh8.cuh) ----
-    DevBuf nodes8;               // [<= T] x 5 float4
-    DevBuf tris8;                // [T] x 3 float4 in wide-leaf order
-    DevBuf wide_bin;             // [<= T] binary node id of each wide node (build scratch)
     // ---- env_shade support ----
     DevBuf lcg_skip;             // [5*N*N+3] x uint2 (mul, add) LCG jump-ahead table for n_samples_x = skip_N
     int skip_N = 0;

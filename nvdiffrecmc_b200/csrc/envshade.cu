@@ -488,7 +488,7 @@ __device__ __forceinline__ bool qslab(const uint4 c, const RayQ &r, float &tn)
 // per visit) the L1 data pipe was a co-limiter at 75 %; quantised nodes took it to 47 % and long-scoreboard stalls from 25 % to
 // 18 % at equal run time; the 4-wide view then halves the visits (13.8 vs 28.8 per ray) for -8 % run time.  Measured and
 // rejected: 4-wide fp32 nodes (7 loads per visit: L1-bound, +5 %), node fetch through the texture path (equal), per-node
-// instead of per-leaf deferral (leaf phase drops to 17 lanes), an 8-wide compressed node (bvh8.cuh: more instructions per ray),
+// instead of per-leaf deferral (leaf phase drops to 17 lanes), an 8-wide compressed node with 8-bit boxes (profiles/r01_bvh8_*: more instructions per ray),
 // sorting the BSDF samples of a pixel by lobe before sampling (one routine per chunk instead of two at 16 lanes: +1.7 %).
 __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, const int warp, const int lane)
 {
