@@ -54,3 +54,75 @@ class GradBucket:
 
     def nbytes(self):
         return self.flat_grad.numel() * self.flat_grad.element_size()
+
+
+# ------------------------------------------------------------------------------------------------
+# Training-loop shim: what train.py:313-494 needs around the kernels to run one process per GPU
+# without editing the reference's files -- rank-consistent randomness, sharded sampling of the view batch, and the all-reduce
+# hooked in front of optimizer.step().
+# ------------------------------------------------------------------------------------------------
+def sync_seed(seed=None, group=None, device=None):
+    """One integer agreed on by all ranks (rank 0's value wins).  The reference draws its per-call seeds from the process-global
+    numpy RNG (render/optixutils/ops.py:83,100) and its per-iteration `rnd_seed` from a module global (render/render.py:19); ranks
+    must use the same stream or the shards stop being shards of ONE Monte-Carlo estimate."""
+    import numpy as np
+    if seed is None:
+        seed = int(np.random.randint(2 ** 31))
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        t = torch.tensor([int(seed)], dtype=torch.int64, device=device if device is not None else "cpu")
+        dist.broadcast(t, src=0, group=group)
+        seed = int(t.item())
+    return int(seed)
+
+
+class StepRNG:
+    """Rank-consistent randomness for the host-side draws of a training step (camera jitter `torch.normal`, render/render.py:50,63;
+    random background, train.py:94): `for_step(it)` returns a generator that is identical on every rank for iteration `it`;
+    `for_view(it, global_view)` one per global view index, so a rank that owns views [a, b) draws exactly what a single process
+    would have drawn for those views."""
+
+    def __init__(self, seed, device="cpu"):
+        self.seed, self.device = int(seed), device
+
+    def _gen(self, *keys):
+        h = self.seed & 0xFFFFFFFF
+        for k in keys:
+            h = (h * 747796405 + 2891336453 + int(k)) & 0xFFFFFFFFFFFFFFFF      # same LCG constants as the kernel's PCG (kernel.cu:33)
+            h ^= h >> 29
+        return torch.Generator(device=self.device).manual_seed(h & 0x7FFFFFFFFFFFFFFF)
+
+    def for_step(self, it):
+        return self._gen(1, it)
+
+    def for_view(self, it, global_view):
+        return self._gen(2, it, global_view)
+
+
+def shard_indices(n_items, global_batch, it, seed, rank=None, world=None):
+    """Dataset indices of THIS rank for iteration `it`: every rank computes the same epoch permutation (seeded by `seed` and the epoch
+    number), the global batch of iteration `it` is a contiguous window of it, and rank r takes `shard_views` of that window.  The union
+    over ranks is exactly the batch a single process with the same seed would load (dataset sampling of train.py:355-360 made
+    rank-consistent)."""
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    per_epoch = max(n_items // global_batch, 1)
+    epoch, k = divmod(int(it), per_epoch)
+    g = torch.Generator().manual_seed((int(seed) * 1000003 + epoch) & 0x7FFFFFFFFFFFFFFF)
+    perm = torch.randperm(n_items, generator=g)
+    window = perm[(k * global_batch) % n_items:(k * global_batch) % n_items + global_batch]
+    if window.numel() < global_batch:                                   # dataset smaller than one batch: wrap around
+        window = torch.cat([window, perm[:global_batch - window.numel()]])
+    return window[shard_views(global_batch, rank, world)]
+
+
+def hook_optimizer(optimizer, bucket, group=None):
+    """Make `optimizer.step()` average the gradient bucket over the ranks first (ONE collective), so the reference's loop body
+    `total_loss.backward(); ...; optimizer.step()` (train.py:438-461) needs no edit.  Returns the optimizer."""
+    inner = optimizer.step
+
+    def step(*a, **k):
+        bucket.all_reduce_mean(group)
+        return inner(*a, **k)
+
+    optimizer.step = step
+    return optimizer

@@ -72,3 +72,72 @@ def test_shard_views_rules():
     assert shard_views(8, rank=0, world=1) == slice(0, 8)
     with pytest.raises(ValueError):
         shard_views(6, rank=0, world=4)
+
+
+def _worker_f1(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nvdiffrecmc_b200.parallel import GradBucket, StepRNG, hook_optimizer, shard_indices, shard_views, sync_seed
+    np.random.seed(100 + rank)                                  # ranks start with DIFFERENT process-global RNG states
+    seed = sync_seed()
+    rng = StepRNG(seed)
+    jitter = torch.normal(0.0, 1.0, (4,), generator=rng.for_step(7))
+    idx = shard_indices(n_items=10, global_batch=4, it=3, seed=seed)
+    sl = shard_views(8)
+    per_view = torch.stack([torch.rand(3, generator=rng.for_view(7, v)) for v in range(sl.start, sl.stop)])
+    # two optimizer steps of the toy problem with the hooked optimizer
+    g = torch.Generator().manual_seed(0)
+    views = torch.rand(8, 32, generator=g)
+    bucket = GradBucket([(32, 3), (32, 3)], device="cpu")
+    with torch.no_grad():
+        bucket.flat.copy_(torch.rand(bucket.flat.numel(), generator=g))
+    opt = hook_optimizer(torch.optim.Adam(bucket.params, lr=0.05), bucket)
+    for _ in range(2):
+        bucket.zero_grad()
+        _toy_loss(bucket.params, views[sl]).backward()
+        opt.step()
+    q.put((rank, seed, jitter.numpy(), idx.numpy(), per_view.numpy(), bucket.flat.detach().clone().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_training_loop_shim_rank_consistency():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_f1, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(2)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, s0, j0, i0, v0, f0), (_, s1, j1, i1, v1, f1) = res
+    assert s0 == s1 and np.array_equal(j0, j1)                                    # one seed, one per-step stream
+    from nvdiffrecmc_b200.parallel import GradBucket, StepRNG, shard_indices
+    full = shard_indices(10, 4, 3, s0, rank=0, world=1).numpy()
+    assert np.array_equal(np.concatenate([i0, i1]), full) and len(set(full.tolist())) == 4       # shards tile the single-process batch
+    rng = StepRNG(s0)
+    assert np.array_equal(np.concatenate([v0, v1]), torch.stack([torch.rand(3, generator=rng.for_view(7, v)) for v in range(8)]).numpy())
+    assert not np.array_equal(v0[0], v0[1])
+    # parameters after two hooked Adam steps == single process on the full batch
+    g = torch.Generator().manual_seed(0)
+    views = torch.rand(8, 32, generator=g)
+    bucket = GradBucket([(32, 3), (32, 3)], device="cpu")
+    with torch.no_grad():
+        bucket.flat.copy_(torch.rand(bucket.flat.numel(), generator=g))
+    opt = torch.optim.Adam(bucket.params, lr=0.05)
+    for _ in range(2):
+        bucket.zero_grad()
+        _toy_loss(bucket.params, views).backward()
+        opt.step()
+    assert np.array_equal(f0, f1) and np.allclose(f0, bucket.flat.detach().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_shard_indices_epochs():
+    from nvdiffrecmc_b200.parallel import shard_indices
+    seen = np.concatenate([shard_indices(12, 4, it, seed=5, rank=0, world=1).numpy() for it in range(3)])
+    assert sorted(seen.tolist()) == list(range(12))                               # one epoch visits every item once
+    nxt = np.concatenate([shard_indices(12, 4, it, seed=5, rank=0, world=1).numpy() for it in range(3, 6)])
+    assert sorted(nxt.tolist()) == list(range(12)) and not np.array_equal(nxt, seen)      # the next epoch is a new permutation
+    assert shard_indices(3, 4, 0, seed=1, rank=0, world=2).numel() == 2           # dataset smaller than the batch wraps around
