@@ -207,9 +207,8 @@ class GpuWorkload:
             timers["fwd1"].record()
         self.seed += 1
         zdz = torch.stack([gb["depth"], torch.full_like(gb["depth"], 0.01)], -1)
-        guide = torch.cat((nrm, zdz), dim=-1)
-        diff, spec = self.denoiser.forward2(torch.cat((diff, guide), dim=-1), torch.cat((spec, guide), dim=-1))   # render.py:120-121
-        shaded = diff * kd * (1.0 - ks[..., 2:3]) + spec                             # render.py:126-127
+        from nvdiffrecmc_b200.denoiser import _safe_normalize
+        shaded = ou.denoise_and_combine(diff, spec, _safe_normalize(nrm), zdz, self.denoiser.sigma, kd, ks)   # render.py:119-127 (+ denoiser.py:28)
         loss = ru.image_loss(shaded, self.target, loss='l1', tonemapper='log_srgb')        # train.py:57-58 ('logl1', the default loss)
         if timers is not None:
             timers["bwd0"].record()

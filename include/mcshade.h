@@ -190,6 +190,14 @@ int mcs_image_loss_bwd(const mcs_tensor *img, const mcs_tensor *target, int32_t 
 int mcs_xfm_fwd(const mcs_tensor *points, const mcs_tensor *matrix, int32_t is_points, float *out, mcs_stream s);
 int mcs_xfm_bwd(const mcs_tensor *points, const mcs_tensor *matrix, const mcs_tensor *d_out, int32_t is_points, float *d_points, mcs_stream s);
 
+/* ---- tail of render.shade() (row f3): normalise the denoiser outputs and recombine the demodulated signals, render/render.py:119-131.
+ *      a4 / b4: [B,H,W,4] raw bilateral outputs (rgb weighted sum, weight) of the diffuse / specular signal; kd, ks [B,H,W,3];
+ *      pbr != 0: out = a.rgb/a.w * kd * (1 - ks.z) + b.rgb/b.w ;  pbr == 0 ('diffuse' / 'white'): out = a.rgb/a.w * kd (b4, ks ignored but
+ *      must be valid views).  Backward writes contiguous gradients for a4, kd (and b4, ks when pbr). */
+int mcs_shade_combine_fwd(const mcs_tensor *a4, const mcs_tensor *b4, const mcs_tensor *kd, const mcs_tensor *ks, int32_t pbr, float *out, mcs_stream s);
+int mcs_shade_combine_bwd(const mcs_tensor *a4, const mcs_tensor *b4, const mcs_tensor *kd, const mcs_tensor *ks, int32_t pbr, const mcs_tensor *d_out,
+                          float *d_a4, float *d_b4, float *d_kd, float *d_ks, mcs_stream s);
+
 /* ---- primary visibility + attribute interpolation: stands in for dr.rasterize / dr.interpolate of nvdiffrast at
  *      the call sites render/render.py:208-234 (closest hit on the context's LBVH instead of rasterisation).
  *      mtx: [B,4,4] row-major fp32 device array, clip = mtx * (p, 1) (inverted on the device, no host round trip).  rast: [B,H,W,4] contiguous, nvdiffrast

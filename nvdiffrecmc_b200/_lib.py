@@ -109,6 +109,8 @@ _SIGS = {
     "mcs_xfm_fwd": ([_T, _T, C.c_int32, _P, _P], C.c_int),
     "mcs_xfm_bwd": ([_T, _T, _T, C.c_int32, _P, _P], C.c_int),
     "mcs_update_pdf": ([_T, _P, _P, _P, _P, _P], C.c_int),
+    "mcs_shade_combine_fwd": ([_T, _T, _T, _T, C.c_int32, _P, _P], C.c_int),
+    "mcs_shade_combine_bwd": ([_T, _T, _T, _T, C.c_int32, _T, _P, _P, _P, _P, _P], C.c_int),
     "mcs_rasterize": ([_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P], C.c_int),
     "mcs_interpolate_fwd": ([_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P], C.c_int),
     "mcs_interpolate_bwd": ([_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P], C.c_int),

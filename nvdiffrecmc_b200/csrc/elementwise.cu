@@ -363,6 +363,54 @@ struct PsnBwd {
 // ---------------------------------------------------------------------------------------------
 // Host-side launch plumbing
 // ---------------------------------------------------------------------------------------------
+// Tail of render.shade(), render/render.py:119-131 (row f3): normalise the two denoiser outputs (rgb weighted sum, weight) and recombine
+// the demodulated signals:  shaded = (A.rgb / A.w) * kd * (1 - ks.z) + B.rgb / B.w   ('pbr');   shaded = (A.rgb / A.w) * kd   ('diffuse' / 'white').
+// One launch instead of ~8 torch element-wise kernels forward and ~14 backward.
+struct CombineFwd {
+    TIn a4, b4, kd, ks; int pbr; float *out;
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
+    {
+        float A[4][4], B[4][4], d[4][3], s[4][3], o[4][3];
+        ew_load<4, FULL>(a4, g, q, A); ew_load<3, FULL>(kd, g, q, d);
+        if (pbr) { ew_load<4, FULL>(b4, g, q, B); ew_load<3, FULL>(ks, g, q, s); }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float ia = 1.0f / A[k][3], m = pbr ? 1.0f - s[k][2] : 1.0f, ib = pbr ? 1.0f / B[k][3] : 0.0f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) o[k][c] = A[k][c] * ia * d[k][c] * m + (pbr ? B[k][c] * ib : 0.0f);
+        }
+        ew_store<3, FULL>(out, q, o);
+    }
+};
+struct CombineBwd {
+    TIn a4, b4, kd, ks, dout; int pbr; float *d_a4, *d_b4, *d_kd, *d_ks;
+    template <bool FULL> __device__ void run(const Grid &g, const Px4 &q) const
+    {
+        float A[4][4], B[4][4], d[4][3], s[4][3], go[4][3], gA[4][4], gB[4][4], gd[4][3], gs[4][3];
+        ew_load<4, FULL>(a4, g, q, A); ew_load<3, FULL>(kd, g, q, d); ew_load<3, FULL>(dout, g, q, go);
+        if (pbr) { ew_load<4, FULL>(b4, g, q, B); ew_load<3, FULL>(ks, g, q, s); }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float ia = 1.0f / A[k][3], m = pbr ? 1.0f - s[k][2] : 1.0f, ib = pbr ? 1.0f / B[k][3] : 0.0f;
+            float gaw = 0.0f, gbw = 0.0f, gm = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float da = A[k][c] * ia;                       // demodulated diffuse
+                gA[k][c] = go[k][c] * d[k][c] * m * ia;
+                gaw -= go[k][c] * d[k][c] * m * da * ia;
+                gd[k][c] = go[k][c] * da * m;
+                gm += go[k][c] * da * d[k][c];
+                gB[k][c] = pbr ? go[k][c] * ib : 0.0f;
+                gbw -= pbr ? go[k][c] * B[k][c] * ib * ib : 0.0f;
+            }
+            gA[k][3] = gaw; gB[k][3] = gbw;
+            gs[k][0] = 0.0f; gs[k][1] = 0.0f; gs[k][2] = pbr ? -gm : 0.0f;
+        }
+        ew_store<4, FULL>(d_a4, q, gA); ew_store<3, FULL>(d_kd, q, gd);
+        if (pbr) { ew_store<4, FULL>(d_b4, q, gB); ew_store<3, FULL>(d_ks, q, gs); }
+    }
+};
+
 struct GridBuilder {
     Grid g{1, 1, 1, 0};
     bool ok = true;
@@ -529,6 +577,19 @@ int mcs_prepare_shading_normal_bwd(const mcs_tensor *pos, const mcs_tensor *view
     IN(pos, pos, 3); IN(view, view_pos, 3); IN(pn, perturbed_nrm, 3); IN(sn, smooth_nrm, 3); IN(st, smooth_tng, 3); IN(gn, geom_nrm, 3); IN(dout, d_out, 3);
     op.two_sided = two_sided_shading; op.opengl = opengl;
     op.d_pos = d_pos; op.d_view = d_view_pos; op.d_pn = d_perturbed_nrm; op.d_sn = d_smooth_nrm; op.d_st = d_smooth_tng; op.d_gn = d_geom_nrm;
+    return launch(op, gb.g, (cudaStream_t)s);
+}
+
+int mcs_shade_combine_fwd(const mcs_tensor *a4, const mcs_tensor *b4, const mcs_tensor *kd, const mcs_tensor *ks, int32_t pbr, float *out, mcs_stream s)
+{
+    GRID(a4, b4, kd, ks); CombineFwd op; IN(a4, a4, 4); IN(b4, b4, 4); IN(kd, kd, 3); IN(ks, ks, 3); op.pbr = pbr; op.out = out;
+    return launch(op, gb.g, (cudaStream_t)s);
+}
+int mcs_shade_combine_bwd(const mcs_tensor *a4, const mcs_tensor *b4, const mcs_tensor *kd, const mcs_tensor *ks, int32_t pbr, const mcs_tensor *d_out,
+                          float *d_a4, float *d_b4, float *d_kd, float *d_ks, mcs_stream s)
+{
+    GRID(a4, b4, kd, ks, d_out); CombineBwd op; IN(a4, a4, 4); IN(b4, b4, 4); IN(kd, kd, 3); IN(ks, ks, 3); IN(dout, d_out, 3); op.pbr = pbr;
+    op.d_a4 = d_a4; op.d_b4 = d_b4; op.d_kd = d_kd; op.d_ks = d_ks;
     return launch(op, gb.g, (cudaStream_t)s);
 }
 

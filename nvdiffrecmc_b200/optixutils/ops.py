@@ -293,3 +293,48 @@ def bilateral_denoiser2(colA, colB, nrm, zdz, sigma):
     """Fused equivalent of (bilateral_denoiser(colA, ...), bilateral_denoiser(colB, ...))."""
     a, b = _bilateral_denoiser2_func.apply(colA, colB, nrm, zdz, sigma)
     return a[..., 0:3] / a[..., 3:4], b[..., 0:3] / b[..., 3:4]
+
+
+# ----------------------------------------------------------------------------------------------
+# Tail of render.shade() (render/render.py:119-131), row f3: denoiser normalisation + demodulated recombination in one launch
+# ----------------------------------------------------------------------------------------------
+class _shade_combine_func(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a4, b4, kd, ks, pbr):
+        L.require_cuda(a4, b4, kd, ks)
+        a4, b4, kd, ks = _f32(a4, "a4"), _f32(b4, "b4"), _f32(kd, "kd"), _f32(ks, "ks")
+        ctx.save_for_backward(a4, b4, kd, ks)
+        ctx.pbr = int(pbr)
+        out = torch.empty(*a4.shape[:3], 3, dtype=torch.float32, device=a4.device)
+        L.check(L.lib().mcs_shade_combine_fwd(C.byref(L.nhwc(a4)), C.byref(L.nhwc(b4)), C.byref(L.nhwc(kd)), C.byref(L.nhwc(ks)), ctx.pbr, out.data_ptr(),
+                                              L.stream_ptr()), "shade_combine (forward)")
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        a4, b4, kd, ks = ctx.saved_tensors
+        shp = a4.shape[:3]
+        d_a4 = torch.empty(*shp, 4, dtype=torch.float32, device=a4.device); d_kd = torch.empty(*shp, 3, dtype=torch.float32, device=a4.device)
+        d_b4 = torch.empty(*shp, 4, dtype=torch.float32, device=a4.device) if ctx.pbr else None
+        d_ks = torch.empty(*shp, 3, dtype=torch.float32, device=a4.device) if ctx.pbr else None
+        g = _f32(dout, "dout")
+        L.check(L.lib().mcs_shade_combine_bwd(C.byref(L.nhwc(a4)), C.byref(L.nhwc(b4)), C.byref(L.nhwc(kd)), C.byref(L.nhwc(ks)), ctx.pbr, C.byref(L.nhwc(g)),
+                                              d_a4.data_ptr(), d_b4.data_ptr() if ctx.pbr else d_a4.data_ptr(), d_kd.data_ptr(),
+                                              d_ks.data_ptr() if ctx.pbr else d_kd.data_ptr(), L.stream_ptr()), "shade_combine (backward)")
+        return d_a4, d_b4, d_kd, d_ks, None
+
+
+def shade_combine(diffuse_w, specular_w, kd, ks, BSDF='pbr'):
+    """diffuse_w / specular_w: RAW [B,H,W,4] bilateral outputs (rgb weighted sum, weight) as returned by the `_func.apply` of the
+    denoiser, kd / ks [B,H,W,3] full-size tensors.  Returns the shaded colour of render.py:123-127 for 'pbr' ('diffuse' / 'white':
+    diffuse only, specular_w / ks unused)."""
+    pbr = BSDF == 'pbr'
+    if not pbr:
+        specular_w, ks = diffuse_w, kd
+    return _shade_combine_func.apply(diffuse_w, specular_w, kd, ks, pbr)
+
+
+def denoise_and_combine(diffuse, specular, nrm, zdz, sigma, kd, ks, BSDF='pbr'):
+    """render.py:119-127 in two launches: the fused two-signal bilateral filter, then normalisation + recombination."""
+    a, b = _bilateral_denoiser2_func.apply(diffuse, specular, nrm, zdz, sigma)
+    return shade_combine(a, b, kd, ks, BSDF)
