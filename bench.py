@@ -188,13 +188,14 @@ class GpuWorkload:
         """One hot-path training iteration.  Returns the loss tensor (device)."""
         torch, ou, wl = self.torch, self.ou, self.wl
         import nvdiffrecmc_b200.renderutils as ru
+        from nvdiffrecmc_b200.raster import texel_fetch
         gb = self.gb
         N = wl["n_samples_x"]
         self.flat_grad.zero_()
         self.lgt.update_pdf()                                                        # train.py:422
         ou.optix_build_bvh(self.ctx, self.verts, self.tris, rebuild=1)               # dlmesh.py:50 (every iteration)
-        kd = self.kd_tex[gb["texel"]]
-        ks = self.ks_tex[gb["texel"]]
+        kd = texel_fetch(self.kd_tex, gb["texel"])                                   # material look-up (stand-in for dr.texture, nearest)
+        ks = texel_fetch(self.ks_tex, gb["texel"])
         nrm = ru.prepare_shading_normal(gb["pos"], gb["view"], None, gb["smooth_nrm"], gb["tangent"], gb["geom_nrm"], two_sided_shading=True,
                                         opengl=True)                                 # render.py:99
         ro = gb["pos"] + nrm * 0.001                                                 # render.py:110

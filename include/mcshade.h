@@ -210,6 +210,11 @@ int mcs_interpolate_fwd(const float *attr, int64_t attr_batch_stride, int32_t V,
 int mcs_interpolate_bwd(const float *attr, int64_t attr_batch_stride, int32_t V, int32_t C, const int32_t *tris, int32_t T, const float *rast,
                         int32_t B, int32_t H, int32_t W, const float *d_out, float *d_attr, mcs_stream stream);
 
+/* Nearest-texel fetch out[i,:] = tex[idx[i],:] (tex [T,C] contiguous, idx int64 [n]; out-of-range indices give zeros) and its scatter-add
+ * backward into a caller-zeroed d_tex [T,C] (float atomics) -- the material look-up of the synthetic G-buffer producer. */
+int mcs_texel_fetch_fwd(const float *tex, int64_t T, int32_t C, const int64_t *idx, int64_t n, float *out, mcs_stream stream);
+int mcs_texel_fetch_bwd(int64_t T, int32_t C, const int64_t *idx, int64_t n, const float *d_out, float *d_tex, mcs_stream stream);
+
 /* ---- env-light pdf / CDF tables: replaces the torch-op chain of EnvironmentLight.update_pdf,
  *      render/light.py:46-59.  base: (1, Hl, Wl, 3) view.  Outputs (caller-allocated, contiguous): pdf [Hl,Wl] normalised to sum 1,
  *      rows [Hl] (what the call site passes as lgt.rows[:,0], render/render.py:114), cols [Hl,Wl]; row_totals: Hl doubles of scratch

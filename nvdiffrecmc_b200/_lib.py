@@ -111,6 +111,8 @@ _SIGS = {
     "mcs_update_pdf": ([_T, _P, _P, _P, _P, _P], C.c_int),
     "mcs_shade_combine_fwd": ([_T, _T, _T, _T, C.c_int32, _P, _P], C.c_int),
     "mcs_shade_combine_bwd": ([_T, _T, _T, _T, C.c_int32, _T, _P, _P, _P, _P, _P], C.c_int),
+    "mcs_texel_fetch_fwd": ([_P, C.c_int64, C.c_int32, _P, C.c_int64, _P, _P], C.c_int),
+    "mcs_texel_fetch_bwd": ([C.c_int64, C.c_int32, _P, C.c_int64, _P, _P, _P], C.c_int),
     "mcs_rasterize": ([_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P], C.c_int),
     "mcs_interpolate_fwd": ([_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P], C.c_int),
     "mcs_interpolate_bwd": ([_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P], C.c_int),

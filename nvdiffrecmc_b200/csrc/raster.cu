@@ -109,6 +109,22 @@ __global__ void __launch_bounds__(256) k_interpolate(const InterpParams p)
     }
 }
 
+// Nearest-texel material fetch (stand-in for dr.texture with filter_mode='nearest', render/texture.py:66-75): out[i,:] = tex[idx[i],:];
+// the backward pass scatters with float atomics (torch's index backward sorts the 2 M indices first and is ~8x slower).
+template <bool BWD>
+__global__ void __launch_bounds__(256) k_texel_fetch(const float *__restrict__ tex, const int64_t *__restrict__ idx, int64_t n, int C, int64_t T,
+                                                     float *__restrict__ out, const float *__restrict__ dout, float *__restrict__ dtex)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t t = __ldg(idx + i);
+    const bool ok = t >= 0 && t < T;
+    for (int c = 0; c < C; ++c) {
+        if (!BWD) out[i * C + c] = ok ? __ldg(tex + t * C + c) : 0.0f;
+        else if (ok) atomicAdd(dtex + t * C + c, __ldg(dout + i * C + c));
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -159,6 +175,24 @@ int mcs_interpolate_bwd(const float *attr, int64_t attr_batch_stride, int32_t V,
     MCS_REQUIRE(d_out && d_attr, "mcs_interpolate_bwd: null gradient pointer");
     p.dout = d_out; p.dattr = d_attr;
     k_interpolate<true><<<(unsigned)((p.npx + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
+    MCS_LAUNCH_CHECK();
+    return 0;
+}
+
+int mcs_texel_fetch_fwd(const float *tex, int64_t T, int32_t C, const int64_t *idx, int64_t n, float *out, mcs_stream stream)
+{
+    MCS_REQUIRE(tex && idx && out && T > 0 && C > 0 && n >= 0, "mcs_texel_fetch_fwd: bad arguments");
+    if (n == 0) return 0;
+    k_texel_fetch<false><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(tex, idx, n, C, T, out, nullptr, nullptr);
+    MCS_LAUNCH_CHECK();
+    return 0;
+}
+
+int mcs_texel_fetch_bwd(int64_t T, int32_t C, const int64_t *idx, int64_t n, const float *d_out, float *d_tex, mcs_stream stream)
+{
+    MCS_REQUIRE(idx && d_out && d_tex && T > 0 && C > 0 && n >= 0, "mcs_texel_fetch_bwd: bad arguments");
+    if (n == 0) return 0;
+    k_texel_fetch<true><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nullptr, idx, n, C, T, nullptr, d_out, d_tex);
     MCS_LAUNCH_CHECK();
     return 0;
 }

@@ -56,3 +56,32 @@ class _interpolate_func(torch.autograd.Function):
 def interpolate(attr, rast, tri):
     """attr [V,C] or [B,V,C], rast from `rasterize`, tri int32 [T,3].  Returns (out [B,H,W,C], None) like dr.interpolate."""
     return _interpolate_func.apply(attr, rast, tri), None
+
+
+class _texel_fetch_func(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tex, idx):
+        L.require_cuda(tex, idx)
+        if idx.dtype != torch.int64:
+            raise TypeError("texel_fetch: idx must be int64")
+        t = tex.to(torch.float32).contiguous(); ix = idx.contiguous()
+        T, Cn = t.shape[0], t.shape[1]
+        out = torch.empty(*ix.shape, Cn, dtype=torch.float32, device=t.device)
+        L.check(L.lib().mcs_texel_fetch_fwd(t.data_ptr(), T, Cn, ix.data_ptr(), ix.numel(), out.data_ptr(), L.stream_ptr()), "texel_fetch (forward)")
+        ctx.save_for_backward(ix)
+        ctx.shape = (T, Cn)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ix,) = ctx.saved_tensors
+        T, Cn = ctx.shape
+        d_tex = torch.zeros(T, Cn, dtype=torch.float32, device=ix.device)
+        g = dout.to(torch.float32).contiguous()
+        L.check(L.lib().mcs_texel_fetch_bwd(T, Cn, ix.data_ptr(), ix.numel(), g.data_ptr(), d_tex.data_ptr(), L.stream_ptr()), "texel_fetch (backward)")
+        return d_tex, None
+
+
+def texel_fetch(tex, idx):
+    """tex [T,C] fp32, idx int64 [...] -> [..., C]; `tex[idx]` with an atomic scatter-add backward (nearest-filter material look-up)."""
+    return _texel_fetch_func.apply(tex, idx)

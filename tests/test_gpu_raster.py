@@ -112,3 +112,18 @@ def test_raster_errors(dev):
         rasterize(ou.OptiXContext(), torch.eye(4, device=dev), (8, 8))
     with pytest.raises(TypeError):
         interpolate(torch.rand(4, 3, device=dev), torch.zeros(1, 2, 2, 4, device=dev), torch.zeros(2, 3, dtype=torch.int64, device=dev))
+
+
+def test_texel_fetch_equals_indexing(dev):
+    from nvdiffrecmc_b200.raster import texel_fetch
+    g = torch.Generator().manual_seed(2)
+    tex = torch.rand(1000, 3, generator=g).to(dev).requires_grad_(True)
+    ref = tex.detach().clone().requires_grad_(True)
+    idx = torch.randint(0, 1000, (2, 33, 17), generator=g).to(dev)
+    out = texel_fetch(tex, idx)
+    assert torch.equal(out, ref[idx])
+    gout = torch.rand(out.shape, generator=g).to(dev)
+    out.backward(gout); ref[idx].backward(gout)
+    assert rel_l2(tex.grad.cpu().numpy(), ref.grad.cpu().numpy()) < 1e-6
+    with pytest.raises(TypeError):
+        texel_fetch(tex, idx.int())
