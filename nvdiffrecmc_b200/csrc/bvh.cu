@@ -16,8 +16,8 @@
 //   5. leaves+refit: padded leaf boxes, sorted triangle records (v0,e1,e2 as 3 x float4), bottom-up
 //                    box union with arrival counters (second thread to arrive continues)
 //   6. emit        : 64-byte fp32 binary traversal nodes holding both children's boxes (stand-alone visibility / closest-hit queries)
-//   7. emit_nodesq : 16-bit quantised child records on a scene-wide power-of-two grid, as a binary (2 x 16 B) and a 4-wide
-//                    (4 x 16 B, the grandchildren) view of the same tree -- what the fused kernel's shadow rays walk
+//   7. emit_nodesq : 16-bit quantised child records on a scene-wide power-of-two grid, as a 4-wide (4 x 16 B: the grandchildren
+//                    of binary node i) view of the same tree -- what the fused kernel's shadow rays walk
 #include <cub/cub.cuh>
 #include "bvh_traverse.cuh"
 #include "ctx.h"
@@ -237,18 +237,19 @@ __global__ void __launch_bounds__(256) k_emit_nodes(int T, const int32_t *__rest
     nodes[4 * (size_t)i + 3] = make_float4(__int_as_float(child_code(c0, T, range)), __int_as_float(child_code(c1, T, range)), 0.0f, 0.0f);
 }
 
-// Quantised copy of the traversal nodes for the shadow rays.  The fused kernel's trace loop is bound by the L1 wavefront queue
-// (every divergent 128-bit load costs one wavefront per distinct line, ~2 cycles each; profiles/r01_v5_*), i.e. by the NUMBER
-// of load instructions per node visit, not by bytes or arithmetic.  A node with both child boxes as 16-bit integers on ONE
-// scene-wide grid is 2 x 16 bytes -- one load per child instead of four per node:
+// Quantised 4-wide view of the tree for the shadow rays.  The fused kernel's trace loop is instruction-issue bound; with fp32
+// 64-byte binary nodes (four loads per visit) the L1 data pipe was a co-limiter as well (75 % busy, profiles/r01_v5_*).  A child
+// record with its box as 16-bit integers on ONE scene-wide grid is 16 bytes -- one 128-bit load per child:
 //   uint4 child = { lo.x | hi.x << 16,  lo.y | hi.y << 16,  lo.z | hi.z << 16,  child code }
+// and node i of the 4-wide view holds the records of the (up to four) GRANDCHILDREN of binary node i: half the visits per ray.
 // Grid: origin = root box min, cell = smallest power of two with 65532 cells covering the root extent (per axis), so
-// cell * (1/d) is exact and the decode is one byte-permute + one FMA per plane (envshade.cu:trace_queue).  Boxes are rounded
-// outward and inflated by two more cells per side, which covers the quantisation rounding and the <= 1-cell error of the
-// biased decode: culling stays conservative, the visibility result is unchanged (tests/test_gpu_envshade.py records test).
+// cell * (1/d) is exact and the decode is one byte-permute + one FMA per plane (envshade.cu:trace_queue); the permute also picks
+// the entry / exit plane by the sign of the ray direction.  Boxes are rounded outward and inflated by two more cells per side,
+// which covers the quantisation rounding and the < 0.51-cell error of the biased decode: culling stays conservative, the
+// visibility result is unchanged (tests/test_gpu_envshade.py records tests, incl. a 330 k-triangle mesh).
 __global__ void __launch_bounds__(256) k_emit_nodesq(int T, const int32_t *__restrict__ left, const int32_t *__restrict__ right,
                                                      const int2 *__restrict__ range, const float *__restrict__ lo, const float *__restrict__ hi,
-                                                     uint4 *__restrict__ nodesq, uint4 *__restrict__ nodesq4, float *__restrict__ qgrid)
+                                                     uint4 *__restrict__ nodesq4, float *__restrict__ qgrid)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float org[3], inv_cell[3];
@@ -268,19 +269,6 @@ __global__ void __launch_bounds__(256) k_emit_nodesq(int T, const int32_t *__res
     int cn[2], code[2];
     if (tiny) { cn[0] = 0; cn[1] = -1; code[0] = ~((0 << 3) | (T - 1)); code[1] = ~0; }
     else { cn[0] = left[i]; cn[1] = right[i]; code[0] = child_code(cn[0], T, range); code[1] = child_code(cn[1], T, range); }
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        uint32_t ql[3], qh[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            if (cn[c] < 0) { ql[a] = 65535u; qh[a] = 0u; continue; }          // unused slot: inverted box, entry > exit for every ray
-            const float fl = floorf(__fmul_rn(__fsub_rn(lo[3 * (size_t)cn[c] + a], org[a]), inv_cell[a])) - 2.0f;
-            const float fh = ceilf(__fmul_rn(__fsub_rn(hi[3 * (size_t)cn[c] + a], org[a]), inv_cell[a])) + 2.0f;
-            ql[a] = (uint32_t)fminf(fmaxf(fl, 0.0f), 65535.0f);
-            qh[a] = (uint32_t)fminf(fmaxf(fh, 0.0f), 65535.0f);
-        }
-        nodesq[2 * (size_t)i + c] = make_uint4(ql[0] | (qh[0] << 16), ql[1] | (qh[1] << 16), ql[2] | (qh[2] << 16), (uint32_t)code[c]);
-    }
     // 4-wide view: node i holds the (up to four) GRANDCHILDREN of binary node i -- a child that is a leaf run stays one slot, an
     // internal child is replaced by its two children.  Same index space as the binary nodes (no allocation; nodes on odd levels
     // are never referenced).  A ray visits ~half as many nodes (13.8 vs 28.8 on the benchmark mesh) and tests fewer boxes (52 vs 58).
@@ -353,7 +341,7 @@ int mcs_ctx_destroy(mcs_ctx *c)
 {
     if (!c) return 0;
     DevBuf *bufs[] = {&c->bounds, &c->tlo, &c->thi, &c->keys, &c->keys_alt, &c->vals, &c->vals_alt, &c->left, &c->right, &c->parent,
-                      &c->lo, &c->hi, &c->flags, &c->range, &c->sort_tmp, &c->nodes, &c->tris, &c->nodesq, &c->nodesq4, &c->qgrid, &c->lcg_skip, &c->light_grad4, &c->mtx_inv};
+                      &c->lo, &c->hi, &c->flags, &c->range, &c->sort_tmp, &c->nodes, &c->tris, &c->nodesq4, &c->qgrid, &c->lcg_skip, &c->light_grad4, &c->mtx_inv};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     delete c;
@@ -385,7 +373,6 @@ int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris
     if (int e = mcs_buf_reserve(c->range, nT * sizeof(int2), s)) return e;
     if (int e = mcs_buf_reserve(c->nodes, nT * 4 * sizeof(float4), s)) return e;
     if (int e = mcs_buf_reserve(c->tris, nT * 3 * sizeof(float4), s)) return e;
-    if (int e = mcs_buf_reserve(c->nodesq, nT * 2 * sizeof(uint4), s)) return e;
     if (int e = mcs_buf_reserve(c->nodesq4, nT * 4 * sizeof(uint4), s)) return e;
     if (int e = mcs_buf_reserve(c->qgrid, 8 * sizeof(float), s)) return e;
 
@@ -418,7 +405,7 @@ int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris
                                                               (const float *)c->lo.p, (const float *)c->hi.p, (float4 *)c->nodes.p);
     MCS_LAUNCH_CHECK();
     k_emit_nodesq<<<nblk(T > 1 ? T - 1 : 1, 256), 256, 0, s>>>(T, (const int32_t *)c->left.p, (const int32_t *)c->right.p, (const int2 *)c->range.p,
-                                                               (const float *)c->lo.p, (const float *)c->hi.p, (uint4 *)c->nodesq.p, (uint4 *)c->nodesq4.p, (float *)c->qgrid.p);
+                                                               (const float *)c->lo.p, (const float *)c->hi.p, (uint4 *)c->nodesq4.p, (float *)c->qgrid.p);
     MCS_LAUNCH_CHECK();
     c->T = T; c->V = V;
     return 0;
@@ -445,7 +432,7 @@ int mcs_trace_visibility(mcs_ctx *c, const float *ro, const float *rd, int64_t n
     MCS_REQUIRE(c && c->T > 0, "mcs_trace_visibility: no acceleration structure built (call mcs_bvh_build first)");
     MCS_REQUIRE(n >= 0 && (n == 0 || (ro && rd && vis)), "mcs_trace_visibility: bad arguments");
     if (n == 0) return 0;
-    VisView b{(const float4 *)c->nodes.p, (const float4 *)c->tris.p, nullptr, nullptr, nullptr};
+    VisView b{(const float4 *)c->nodes.p, (const float4 *)c->tris.p, nullptr, nullptr};
     k_visibility<<<nblk(n, 128), 128, 0, (cudaStream_t)stream>>>(b, ro, rd, n, vis);
     MCS_LAUNCH_CHECK();
     return 0;
@@ -456,7 +443,7 @@ int mcs_trace_closest(mcs_ctx *c, const float *ro, const float *rd, int64_t n, i
     MCS_REQUIRE(c && c->T > 0, "mcs_trace_closest: no acceleration structure built (call mcs_bvh_build first)");
     MCS_REQUIRE(n >= 0 && (n == 0 || (ro && rd && tri_id && tuv)), "mcs_trace_closest: bad arguments");
     if (n == 0) return 0;
-    BvhView b{(const float4 *)c->nodes.p, (const float4 *)c->tris.p, nullptr, nullptr, nullptr};
+    BvhView b{(const float4 *)c->nodes.p, (const float4 *)c->tris.p, nullptr, nullptr};
     k_closest<<<nblk(n, 128), 128, 0, (cudaStream_t)stream>>>(b, ro, rd, n, tri_id, tuv);
     MCS_LAUNCH_CHECK();
     return 0;

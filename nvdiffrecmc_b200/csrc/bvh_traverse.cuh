@@ -29,7 +29,6 @@ __device__ __forceinline__ F8 ldg256(const void *p)
 struct BvhView {
     const float4 *nodes;
     const float4 *tris;
-    const uint4 *nodesq;     // 32-byte quantised nodes (one 128-bit load per child), see bvh.cu:k_emit_nodesq; may be null
     const float *qgrid;      // origin xyz, cell xyz of the quantisation grid
     const uint4 *nodesq4;    // 64-byte 4-wide quantised nodes (bvh.cu:k_emit_nodesq, wide part); may be null
 };

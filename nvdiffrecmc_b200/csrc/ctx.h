@@ -27,8 +27,7 @@ struct mcs_ctx {
     // ---- traversal layout ----
     DevBuf nodes;                // [max(T-1,1)] x 4 float4 (two child boxes + child codes)
     DevBuf tris;                 // [T] x 3 float4 in SORTED order: (v0, orig id), (e1, -), (e2, -)
-    DevBuf nodesq;               // [max(T-1,1)] x 2 uint4: the same nodes with 16-bit boxes on a global power-of-two grid (shadow rays)
-    DevBuf nodesq4;              // [max(T-1,1)] x 4 uint4: 4-wide view (the <= 4 grandchildren of binary node i), same child records
+    DevBuf nodesq4;              // [max(T-1,1)] x 4 uint4: 4-wide quantised view (the <= 4 grandchildren of binary node i), 16-bit boxes on a scene-wide grid
     DevBuf qgrid;                // 6 floats: grid origin xyz, cell size xyz
     // ---- env_shade support ----
     DevBuf lcg_skip;             // [5*N*N+3] x uint2 (mul, add) LCG jump-ahead table for n_samples_x = skip_N

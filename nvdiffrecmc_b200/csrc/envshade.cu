@@ -275,9 +275,6 @@ __device__ __forceinline__ float warp_sum(float v)
 #ifndef MCS_REPLAY_MINB
 #define MCS_REPLAY_MINB 3                // replay kernel: 80 registers, 3 CTAs/SM (2.93 -> 2.54 ms on 4 views; 4 CTAs/SM spills, software prefetch was slower)
 #endif
-#ifndef MCS_WIDE4
-#define MCS_WIDE4 1                      // shadow rays walk the 4-wide view of the quantised nodes (64 B, half the visits)
-#endif
 #ifndef MCS_CTA_WARPS
 #define MCS_CTA_WARPS 8
 #endif
@@ -290,7 +287,7 @@ __device__ __forceinline__ float warp_sum(float v)
 constexpr int NW = MCS_CTA_WARPS;
 constexpr int SEG = 128;                 // queue entries per warp segment (= one pixel at N = 8)
 constexpr int QTOT = NW * SEG;
-constexpr int PCAP = MCS_WIDE4 ? 160 : 96;   // pending (ray, leaf) pairs per warp: < 32 carried over + at most 64 (binary) / 128 (4-wide) appended per node step
+constexpr int PCAP = 160;                // pending (ray, leaf) pairs per warp: < 32 carried over + at most 128 appended per node step
 constexpr int PIXRING = 256;
 static_assert(QTOT <= 65536, "queue entry index is stored in 16 bits");
 static_assert(SEG <= 256 && SEG % 32 == 0, "sample slot within a fill is stored in 8 bits");
@@ -499,7 +496,7 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
     int pend = 0;
     int my = -1;
     int node = 0, sp = 0;
-    int stack[MCS_WIDE4 ? 96 : MCS_STACK];       // 4-wide: up to 3 pushes per visit (1.5 per binary level)
+    int stack[96];                               // up to 3 pushes per visit (1.5 per binary level; MCS_STACK = 64 covers the binary walk)
     RayQ r; r.ax = r.ay = r.az = 1.0f; r.bx = r.by = r.bz = 0.0f; r.nx = r.ny = r.nz = 0x7410u;
     const BvhView b = p.bvh;
     uint2 *pl = q.pl[warp];
@@ -561,7 +558,6 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
         }
         const int thresh = exhausted < NW ? REFILL_BELOW : 1;
         do {
-#if MCS_WIDE4
             const int cur = my;
             unsigned lmask = 0u;
             int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
@@ -597,37 +593,6 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
                 }
                 pend += __popc(mL);
             }
-#else
-            const int cur = my;
-            unsigned lmask = 0u;
-            int ch0 = 0, ch1 = 0;
-            if (my >= 0) {
-                const uint4 *n = b.nodesq + 2 * (size_t)node;
-                const uint4 k0 = __ldg(n), k1 = __ldg(n + 1);
-                float tn0, tn1;
-                const bool h0 = qslab(k0, r, tn0), h1 = qslab(k1, r, tn1);
-                ch0 = (int)k0.w; ch1 = (int)k1.w;
-                lmask = (h0 && ch0 < 0 ? 1u : 0u) | (h1 && ch1 < 0 ? 2u : 0u);
-                // descend / push / pop with selects; the nearer internal child first (occluders close to the origin end the ray early)
-                const bool i0 = h0 && ch0 >= 0, i1 = h1 && ch1 >= 0;
-                const bool both = i0 && i1, first0 = tn0 <= tn1;
-                if (both) stack[sp] = first0 ? ch1 : ch0;
-                sp += both ? 1 : 0;
-                const int nxt = (both ? first0 : i0) ? ch0 : ch1;
-                if (i0 || i1) node = nxt;
-                else if (sp) node = stack[--sp];
-                else my = -1;                               // walk finished; verdict comes from the occluded bit
-            }
-            // defer the leaf tests: one (ray, leaf run) pair per leaf child hit; a second ballot only when some lane hit two
-            const unsigned mL = __ballot_sync(0xFFFFFFFFu, lmask != 0u);
-            if (lmask) pl[pend + __popc(mL & lt)] = make_uint2((unsigned)cur, (unsigned)((lmask & 1u) ? ch0 : ch1));
-            pend += __popc(mL);
-            const unsigned m2 = __ballot_sync(0xFFFFFFFFu, lmask == 3u);
-            if (m2) {
-                if (lmask == 3u) pl[pend + __popc(m2 & lt)] = make_uint2((unsigned)cur, (unsigned)ch1);
-                pend += __popc(m2);
-            }
-#endif
             nact = __popc(__ballot_sync(0xFFFFFFFFu, my >= 0));
         } while (pend < LEAF_BATCH && nact >= thresh);
         while (pend >= LEAF_BATCH) leaf_batch(32);
@@ -1004,7 +969,7 @@ static int fill_params(mcs_ctx *ctx, EnvParams &p,
     p.perms = (const int32_t *)perms->ptr; p.pm_s1 = perms->strides[1]; p.pm_s3 = perms->strides[3]; p.n_perms = (uint32_t)perms->sizes[1];
     p.m_rows = cdf_iters(p.Hl); p.m_cols = cdf_iters(p.Wl);
     p.bsdf = bsdf; p.seed = rnd_seed; p.batch_offset = batch_offset; p.shadow_scale = shadow_scale;
-    p.bvh = BvhView{(const float4 *)ctx->nodes.p, (const float4 *)ctx->tris.p, (const uint4 *)ctx->nodesq.p, (const float *)ctx->qgrid.p, (const uint4 *)ctx->nodesq4.p};
+    p.bvh = BvhView{(const float4 *)ctx->nodes.p, (const float4 *)ctx->tris.p, (const float *)ctx->qgrid.p, (const uint4 *)ctx->nodesq4.p};
     if (int e = ensure_skip_table(ctx, p.N, s)) return e;
     p.skip = (const uint2 *)((const char *)ctx->lcg_skip.p);
     if (int e = mcs_buf_reserve(ctx->light_grad4, 256, s)) return e;

@@ -138,7 +138,7 @@ int mcs_rasterize(mcs_ctx *c, const float *mtx, int32_t B, int32_t H, int32_t W,
     k_invert4<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(mtx, inv_mtx, B);
     MCS_LAUNCH_CHECK();
     RasterParams p{};
-    p.bvh = BvhView{(const float4 *)c->nodes.p, (const float4 *)c->tris.p, nullptr, nullptr, nullptr};
+    p.bvh = BvhView{(const float4 *)c->nodes.p, (const float4 *)c->tris.p, nullptr, nullptr};
     p.mtx = mtx; p.inv = inv_mtx; p.B = B; p.H = H; p.W = W; p.rast = rast;
     const int64_t n = (int64_t)B * H * W;
     k_rasterize<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
