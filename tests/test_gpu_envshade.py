@@ -212,3 +212,53 @@ def test_records_on_a_large_mesh(dev):
     traced = rec_v != 2
     assert np.array_equal(rec_v[traced], rv[traced]) and (rv[traced] == 0).sum() > 100
     assert rel_l2(diff.cpu().numpy(), d_ref) < TOL and rel_l2(spec.cpu().numpy(), s_ref) < TOL
+
+
+@pytest.mark.parametrize("n_occ", [0, 1, 3, 6])
+def test_tiny_and_flat_meshes(dev, n_occ):
+    """1-4 triangles take the 'root is one leaf run' path of the node emitters; an axis-aligned plane has zero extent in one axis
+    (degenerate quantisation grid); with occluders hovering above the plane some shadow rays are blocked.  Bit-exact vs brute force."""
+    from nvdiffrecmc_b200.optixutils.ops import env_shade_records
+    import nvdiffrecmc_b200.optixutils as ou
+    rng = np.random.default_rng(n_occ)
+    v = [[-2, 0, -2], [2, 0, -2], [2, 0, 2], [-2, 0, 2]]
+    f = [[0, 1, 2], [0, 2, 3]] if n_occ != 0 else [[0, 1, 2]]
+    for k in range(n_occ):
+        c = rng.uniform(-1, 1, 3) * [1.0, 0.0, 1.0] + [0, 0.4 + 0.2 * k, 0]
+        b = len(v)
+        v += [list(c + [-0.6, 0, -0.5]), list(c + [0.6, 0.05, -0.4]), list(c + [0.0, 0.0, 0.7])]
+        f.append([b, b + 1, b + 2])
+    v = np.asarray(v, np.float32); f = np.asarray(f, np.int32)
+    if n_occ == 0:
+        assert f.shape[0] == 1
+    H = W = 12
+    N = 4
+    xs = np.linspace(-0.9, 0.9, W, dtype=np.float32)
+    gx, gz = np.meshgrid(xs, xs, indexing="xy")
+    pos = np.stack([gx, np.zeros((H, W), np.float32), gz], -1)[None].astype(np.float32)                   # points on the plane y = 0
+    if n_occ == 0:
+        pos = pos * np.float32(0.4) + np.float32([0.6, 0, -0.6])       # stay inside the single triangle
+    nrm = np.zeros_like(pos); nrm[..., 1] = 1
+    view = np.float32([0.3, 2.0, 0.4]).reshape(1, 1, 1, 3)
+    kd = rng.uniform(0.1, 1, pos.shape).astype(np.float32); ks = rng.uniform(0.1, 1, pos.shape).astype(np.float32); ks[..., 0] = 0
+    mask = np.ones((1, H, W), np.float32)
+    ro = (pos + nrm * np.float32(0.001)).astype(np.float32)
+    o = oracle()
+    from nvdiffrecmc_b200 import synth
+    light = synth.random_light(32, seed=3)
+    pdf, rows, cols = o.update_pdf(light)
+    perms = synth.make_perms(N, seed=4, rows=128)
+    ctx = ou.OptiXContext()
+    ou.optix_build_bvh(ctx, torch.tensor(v, device=dev), torch.tensor(f, device=dev), rebuild=1)
+    t = lambda a: torch.tensor(a, device=dev)
+    diff, spec, rec_t, rec_v = env_shade_records(ctx, t(mask), t(ro), t(pos), t(nrm), t(view), t(kd), t(ks), t(light), t(pdf), t(rows), t(cols), t(perms),
+                                                 BSDF="pbr", n_samples_x=N, rnd_seed=2, shadow_scale=1.0)
+    d_ref, s_ref, (rt, rv) = o.env_shade(o.scene(v, f), mask, ro, pos, nrm, view, kd, ks, light, pdf, rows, cols, perms, BSDF="pbr", n_samples_x=N,
+                                         rnd_seed=2, records=True)
+    rec_t, rec_v = rec_t.cpu().numpy(), rec_v.cpu().numpy()
+    assert np.array_equal(rec_t, rt)
+    traced = rec_v != 2
+    assert np.array_equal(rec_v[traced], rv[traced])
+    if n_occ >= 3:
+        assert (rv[traced] == 0).sum() > 20                      # some rays really are occluded
+    assert rel_l2(diff.cpu().numpy(), d_ref) < TOL and rel_l2(spec.cpu().numpy(), s_ref) < TOL
