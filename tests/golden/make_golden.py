@@ -111,3 +111,44 @@ def make_loss_xfm():
 
 if __name__ == "__main__":
     make_loss_xfm()
+
+
+def make_update_pdf():
+    """Row a17: EnvironmentLight.update_pdf (render/light.py:46-59) and util.pixel_grid (render/util.py:62-66).  Neither module can be
+    imported here (nvdiffrast / imageio at import time, device="cuda" literals), so the two function bodies are taken from the files'
+    ASTs at generation time, `device="cuda"` is rewritten to "cpu", and they run unmodified otherwise.  Nothing is copied into the repo."""
+    import types
+
+    def extract(path, want):
+        tree = ast.parse(open(path).read())
+        found = {}
+        for node in ast.walk(tree):
+            if isinstance(node, ast.FunctionDef) and node.name in want:
+                found[node.name] = node
+        return found
+
+    class Cpu(ast.NodeTransformer):
+        def visit_Constant(self, n):
+            return ast.copy_location(ast.Constant("cpu"), n) if n.value == "cuda" else n
+
+    pg = Cpu().visit(extract(os.path.join(REF, "render", "util.py"), {"pixel_grid"})["pixel_grid"])
+    up = Cpu().visit(extract(os.path.join(REF, "render", "light.py"), {"update_pdf"})["update_pdf"])
+    mod = ast.Module(body=[pg, up], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    ns = {"torch": torch, "np": np}
+    exec(compile(mod, "<reference update_pdf>", "exec"), ns)
+    ns["util"] = types.SimpleNamespace(pixel_grid=ns["pixel_grid"])
+    out = {}
+    g = torch.Generator().manual_seed(21)
+    for name, hw in (("a", (16, 32)), ("b", (64, 64))):
+        base = torch.rand(hw[0], hw[1], 3, generator=g) ** 3 * 10
+        base[hw[0] // 4] = 0                                   # an all-black row exercises the `> 0` guards (light.py:58-59)
+        self = types.SimpleNamespace(base=base)
+        ns["update_pdf"](self)
+        out.update({name + "_base": base.numpy(), name + "_pdf": self._pdf.numpy(), name + "_cols": self.cols.numpy(), name + "_rows": self.rows.numpy()})
+    np.savez_compressed(os.path.join(OUT, "ref_update_pdf.npz"), **out)
+    print("wrote ref_update_pdf")
+
+
+if __name__ == "__main__":
+    make_update_pdf()

@@ -62,3 +62,14 @@ def test_env_shade_consumes_native_tables(dev):
                               lgt.cols, BSDF='diffuse', n_samples_x=N, rnd_seed=3, perms=perms)
     # diffuse-only: integral of L * cos/pi over the hemisphere = L
     assert abs(float(d.mean()) / 0.7 - 1) < 0.05
+
+
+def test_update_pdf_matches_reference_golden(dev):
+    """The native kernel against the output of the reference's own update_pdf (tests/golden/ref_update_pdf.npz)."""
+    import os
+    from nvdiffrecmc_b200.light import EnvironmentLight
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_update_pdf.npz"))
+    for k in ("a", "b"):
+        lgt = EnvironmentLight(torch.tensor(d[k + "_base"], device=dev))
+        assert rel_l2(lgt._pdf.cpu().numpy(), d[k + "_pdf"]) < 2e-6 and rel_l2(lgt.cols.cpu().numpy(), d[k + "_cols"]) < 2e-6
+        assert rel_l2(lgt.rows.cpu().numpy(), d[k + "_rows"]) < 2e-6 and tuple(lgt.rows.shape) == d[k + "_rows"].shape
