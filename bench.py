@@ -305,21 +305,37 @@ def traversal_counts(wl, sample_res=64):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step(o, case, N, sigma, seed):
-    """The same hot-path step on the host CPUs through the oracle (all OpenMP threads)."""
+def cpu_reference(o):
+    """(env_shade callable, kind): the reference's own raygen program compiled for the host (oracle/_ref, built where /root/reference
+    exists and shipped as a prebuilt library) when available, else the oracle port."""
+    try:
+        from oracle import Reference
+        ref = Reference(o)
+        return ref.env_shade, "reference"
+    except Exception:
+        return o.env_shade, "port"
+
+
+def cpu_reference_step(o, case, N, sigma, seed, env_shade=None):
+    """The same hot-path step on the host CPUs (all OpenMP threads): env_shade forward + backward through `env_shade` (the compiled
+    reference or the oracle port), LBVH rebuild / shading normal / denoiser / update_pdf through the oracle port."""
     c = case
+    es = env_shade if env_shade is not None else o.env_shade
     scene = o.scene(c["verts"], c["tris"])                                       # LBVH rebuild every iteration
     nrm = o.prepare_shading_normal(c["pos"], c["view"], None, c["smooth_nrm"], c["tangent"], c["geom_nrm"])
     ro = (c["pos"] + nrm * np.float32(0.001)).astype(np.float32)
     pdf, rows, cols = o.update_pdf(c["light"])
     args = (scene, c["mask"], ro, c["pos"], nrm, c["view"], c["kd"], c["ks"], c["light"], pdf, rows, cols, c["perms"])
-    d, s = o.env_shade(*args, n_samples_x=N, rnd_seed=seed, vis_mode="bvh")
+    d, s = es(*args, n_samples_x=N, rnd_seed=seed, vis_mode="bvh")
     zdz = np.stack([c["depth"], np.full_like(c["depth"], 0.01)], -1)
     nn = nrm / np.maximum(np.linalg.norm(nrm, axis=-1, keepdims=True), 1e-20)
     fd, fs = o.bilateral_fwd(d, nn, zdz, sigma), o.bilateral_fwd(s, nn, zdz, sigma)
     gd = np.concatenate([np.ones_like(d) / fd[..., 3:], np.zeros_like(fd[..., 3:])], -1)
     cd, cs = o.bilateral_bwd(nn, zdz, sigma, gd), o.bilateral_bwd(nn, zdz, sigma, gd)
-    g = o.env_shade(*args, n_samples_x=N, rnd_seed=seed, vis_mode="bvh", grads=(cd, cs), parallel_bwd=True)
+    if es is o.env_shade:
+        g = es(*args, n_samples_x=N, rnd_seed=seed, vis_mode="bvh", grads=(cd, cs), parallel_bwd=True)
+    else:
+        g = es(*args, n_samples_x=N, rnd_seed=seed, vis_mode="bvh", grads=(cd, cs))
     o.prepare_shading_normal_bwd(c["pos"], c["view"], None, c["smooth_nrm"], c["tangent"], c["geom_nrm"], g[1])
     return float(d.sum())
 
@@ -340,6 +356,14 @@ def host_cores():
     return n
 
 
+REF_ARM_NOTE = {
+    "reference": "env_shade forward + backward = the reference's own raygen program (render/optixutils/c_src/envsampling/kernel.cu with bsdf.h, "
+                 "math_utils.h) compiled for the host cores (oracle/_ref, OpenMP over pixels), shadow rays answered by the oracle's LBVH (OptiX itself "
+                 "is closed source and needs an RT driver); denoiser / shading normal / update_pdf / LBVH build = oracle C port",
+    "port": "CPU oracle port of kernel.cu/denoising.cu/normal.cu (oracle/_ref not available on this machine; OptiX needs libnvoptix + RT driver)",
+}
+
+
 def run_reference(args, wl):
     """--impl reference: the reference's algorithm on the host CPUs (oracle port; OptiX cannot be built/run here)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -349,16 +373,17 @@ def run_reference(args, wl):
     from common import make_case, oracle
     o = oracle()
     cores = o.set_threads(cores)
+    es, kind = cpu_reference(o)
     N, res_s = wl["n_samples_x"], 128
     case = make_case(res=res_s, B=1, N=N, mesh=wl["mesh"], level=wl["mesh_level"], light="random", light_hw=(wl["light_res"], wl["light_res"]),
                      perm_rows=4096)
     covered = int((case["mask"] > 0).sum())
     rays_step = covered * 2 * N * N * 2
     for i in range(args.warmup):
-        cpu_reference_step(o, case, N, wl["sigma"], i)
+        cpu_reference_step(o, case, N, wl["sigma"], i, es)
     t0 = time.time()
     for i in range(args.steps):
-        cpu_reference_step(o, case, N, wl["sigma"], 100 + i)
+        cpu_reference_step(o, case, N, wl["sigma"], 100 + i, es)
     dt = (time.time() - t0) / args.steps
     val = rays_step / dt / 1e6
     sample = "1 view at %dx%d of the same scene (same mesh, probe, n_samples_x=%d, sigma=%g): %d rays/step" % (res_s, res_s, N, wl["sigma"], rays_step)
@@ -366,8 +391,8 @@ def run_reference(args, wl):
         "impl": "reference", "metric": "shadow_rays_per_second_train_step", "value": round(val, 4), "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "reference_arm": "CPU oracle port of kernel.cu/denoising.cu/normal.cu (OptiX needs libnvoptix + RT driver; not buildable here)"},
-        "cpu_baseline": {"value": round(val, 4), "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": wl["name"], "reference_arm": REF_ARM_NOTE[kind]},
+        "cpu_baseline": {"value": round(val, 4), "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": round(val, 4), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "iters_per_s_on_sample": round(1.0 / dt, 4),
     })
@@ -570,17 +595,18 @@ def main():
         from common import make_case, oracle
         o = oracle()
         ncores = o.set_threads(ncores)
+        es, kind = cpu_reference(o)
         res_s = 96
         case = make_case(res=res_s, B=1, N=N, mesh=wl["mesh"], level=wl["mesh_level"], light="random", light_hw=(wl["light_res"], wl["light_res"]),
                          perm_rows=4096)
         cov = int((case["mask"] > 0).sum())
-        cpu_reference_step(o, case, N, wl["sigma"], 0)
+        cpu_reference_step(o, case, N, wl["sigma"], 0, es)
         t0 = time.time(); reps = 2
         for i in range(reps):
-            cpu_reference_step(o, case, N, wl["sigma"], 1 + i)
+            cpu_reference_step(o, case, N, wl["sigma"], 1 + i, es)
         dt = (time.time() - t0) / reps
-        cpu = {"value": round(cov * 2 * N * N * 2 / dt / 1e6, 4), "unit": "Mrays/s", "cores": ncores, "kind": "port",
-               "sample": "same step on 1 view at %dx%d (%d rays/step), oracle C port with OpenMP" % (res_s, res_s, cov * 2 * N * N * 2)}
+        cpu = {"value": round(cov * 2 * N * N * 2 / dt / 1e6, 4), "unit": "Mrays/s", "cores": ncores, "kind": kind,
+               "sample": "same step on 1 view at %dx%d (%d rays/step), OpenMP; %s" % (res_s, res_s, cov * 2 * N * N * 2, REF_ARM_NOTE[kind])}
 
     out = {
         "metric": "shadow_rays_per_second_train_step", "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,

@@ -5,6 +5,10 @@ restates and how it is pinned).  Only ``tests/``, ``__graft_entry__.smoke()`` an
 ``cpu_baseline`` / ``--impl reference`` legs may import this package; ``nvdiffrecmc_b200`` never
 does.
 
+``build_ref()`` / ``Reference`` compile and drive the reference's OWN raygen source on the CPU (oracle/ref_shim -> oracle/_ref, only
+where /root/reference exists; the built library is git-ignored and travels to the GPU box) -- the check of this restatement
+against the reference itself, and the `--impl reference` arm of bench.py.
+
 Two builds of the same source exist: fp32 (the oracle proper, ``Oracle()``) and fp64
 (``Oracle(f64=True)``), the latter used only to validate the hand-derived adjoints by finite
 differences.
@@ -48,6 +52,69 @@ def build(force=False):
         if f64:
             cmd.insert(1, "-DORACLE_F64")
         subprocess.run(cmd, check=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle/_ref: the UNMODIFIED reference raygen program compiled for the host (oracle/ref_shim/), only where /root/reference exists
+# ------------------------------------------------------------------------------------------------
+REF_KERNEL = "/root/reference/render/optixutils/c_src/envsampling/kernel.cu"
+_REF_DIR = os.path.join(_HERE, "_ref")
+_REF_LIB = os.path.join(_REF_DIR, "libref_envshade.so")
+_SHIM = os.path.join(_HERE, "ref_shim")
+
+
+def build_ref(force=False):
+    """g++ on the reference's own kernel.cu (and the headers it includes) where it lies, through the host shim.  Returns the library path,
+    or None when the reference tree is not present (GPU box) and no prebuilt library travelled with the snapshot."""
+    if not os.path.exists(REF_KERNEL):
+        return _REF_LIB if os.path.exists(_REF_LIB) else None
+    srcs = [os.path.join(_SHIM, "ref_env_shade.cpp"), os.path.join(_SHIM, "optix.h"), REF_KERNEL]
+    if not force and os.path.exists(_REF_LIB) and all(os.path.getmtime(_REF_LIB) >= os.path.getmtime(s) for s in srcs):
+        return _REF_LIB
+    os.makedirs(_REF_DIR, exist_ok=True)
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-w", "-I" + cuda_inc, "-I" + _SHIM,
+           "-I" + os.path.dirname(REF_KERNEL), '-DREF_KERNEL="%s"' % REF_KERNEL, srcs[0], "-o", _REF_LIB]
+    subprocess.run(cmd, check=True)
+    return _REF_LIB
+
+
+class Reference:
+    """The reference's own __raygen__rg / process_sample (kernel.cu:403-542) running on the CPU.  Visibility comes from `scene`
+    (an fp32 oracle Scene): OptiX itself is closed source.  Raises RuntimeError when oracle/_ref cannot be built or found."""
+
+    def __init__(self, orc):
+        path = build_ref()
+        if path is None:
+            raise RuntimeError("oracle/_ref unavailable: /root/reference is not present and no prebuilt libref_envshade.so was found")
+        assert not orc.f64, "the reference kernel is fp32"
+        self.orc = orc
+        self.lib = C.CDLL(path)
+        self.lib.ref_set_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        self.lib.ref_env_shade.argtypes = [C.c_int] * 7 + [C.c_uint, C.c_uint, C.c_float, C.c_int] + [C.c_void_p] * 21
+
+    def env_shade(self, scene, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms, BSDF="pbr", n_samples_x=8,
+                  rnd_seed=0, shadow_scale=1.0, grads=None, vis_mode="brute"):
+        """Forward -> (diff, spec); with grads=(diff_grad, spec_grad) -> (pos_grad, nrm_grad, kd_grad, ks_grad, light_grad)."""
+        f = lambda a: np.ascontiguousarray(a, np.float32)
+        mask, ro, gb_pos, gb_normal, gb_kd, gb_ks = [f(a) for a in (mask, ro, gb_pos, gb_normal, gb_kd, gb_ks)]
+        B, H, W = mask.shape
+        view = np.ascontiguousarray(np.broadcast_to(f(gb_view_pos), (B, 1, 1, 3)))
+        light, pdf, rows, cols = f(light), f(pdf), f(rows), f(cols)
+        perms = np.ascontiguousarray(perms, np.int32)
+        assert perms.shape[1] == n_samples_x * n_samples_x
+        Hl, Wl = light.shape[:2]
+        z4 = lambda: np.zeros((B, H, W, 3), np.float32)
+        diff, spec = z4(), z4()
+        dg, sg = (f(grads[0]), f(grads[1])) if grads is not None else (z4(), z4())
+        pg, ng, kg, sgd, lg = z4(), z4(), z4(), z4(), np.zeros((Hl, Wl, 3), np.float32)
+        occ = C.cast(self.orc.lib.orc_occluded1, C.c_void_p)
+        self.lib.ref_set_visibility(occ, scene.h, {"brute": 0, "bvh": 1}[vis_mode])
+        p = lambda a: a.ctypes.data
+        self.lib.ref_env_shade(B, H, W, Hl, Wl, perms.shape[0], n_samples_x, BSDF_MODES.index(BSDF), int(rnd_seed) & 0xFFFFFFFF, float(shadow_scale),
+                               0 if grads is None else 1, p(mask), p(ro), p(gb_pos), p(gb_normal), p(view), p(gb_kd), p(gb_ks), p(light), p(pdf), p(rows),
+                               p(cols), p(perms), p(diff), p(spec), p(dg), p(sg), p(pg), p(ng), p(kg), p(sgd), p(lg))
+        return (diff, spec) if grads is None else (pg, ng, kg, sgd, lg)
 
 
 def _envshade_struct(real):

@@ -20,7 +20,9 @@ def test_reference_arm_prints_one_json_line():
               "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "Mrays/s" and d["higher_is_better"] is True and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import build_ref
+    assert d["cpu_baseline"]["kind"] == ("reference" if build_ref() else "port")      # oracle/_ref is used whenever it exists
     assert d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
     import bench
     assert d["cpu_baseline"]["cores"] == bench.host_cores()     # not the 1 thread of the inherited OMP_NUM_THREADS
