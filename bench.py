@@ -306,21 +306,21 @@ def traversal_counts(wl, sample_res=64):
 
 # ------------------------------------------------------------------------------------------------
 def cpu_reference(o):
-    """(env_shade callable, kind): the reference's own raygen program compiled for the host (oracle/_ref, built where /root/reference
-    exists and shipped as a prebuilt library) when available, else the oracle port."""
+    """(object with env_shade / bilateral_fwd / bilateral_bwd, kind): the reference's own raygen program and denoiser kernels compiled for
+    the host (oracle/_ref, built where /root/reference exists and shipped as a prebuilt library) when available, else the oracle port."""
     try:
         from oracle import Reference
-        ref = Reference(o)
-        return ref.env_shade, "reference"
+        return Reference(o), "reference"
     except Exception:
-        return o.env_shade, "port"
+        return o, "port"
 
 
 def cpu_reference_step(o, case, N, sigma, seed, env_shade=None):
     """The same hot-path step on the host CPUs (all OpenMP threads): env_shade forward + backward through `env_shade` (the compiled
     reference or the oracle port), LBVH rebuild / shading normal / denoiser / update_pdf through the oracle port."""
     c = case
-    es = env_shade if env_shade is not None else o.env_shade
+    impl = env_shade if env_shade is not None else o
+    es = impl.env_shade
     scene = o.scene(c["verts"], c["tris"])                                       # LBVH rebuild every iteration
     nrm = o.prepare_shading_normal(c["pos"], c["view"], None, c["smooth_nrm"], c["tangent"], c["geom_nrm"])
     ro = (c["pos"] + nrm * np.float32(0.001)).astype(np.float32)
@@ -329,10 +329,10 @@ def cpu_reference_step(o, case, N, sigma, seed, env_shade=None):
     d, s = es(*args, n_samples_x=N, rnd_seed=seed, vis_mode="bvh")
     zdz = np.stack([c["depth"], np.full_like(c["depth"], 0.01)], -1)
     nn = nrm / np.maximum(np.linalg.norm(nrm, axis=-1, keepdims=True), 1e-20)
-    fd, fs = o.bilateral_fwd(d, nn, zdz, sigma), o.bilateral_fwd(s, nn, zdz, sigma)
+    fd, fs = impl.bilateral_fwd(d, nn, zdz, sigma), impl.bilateral_fwd(s, nn, zdz, sigma)
     gd = np.concatenate([np.ones_like(d) / fd[..., 3:], np.zeros_like(fd[..., 3:])], -1)
-    cd, cs = o.bilateral_bwd(nn, zdz, sigma, gd), o.bilateral_bwd(nn, zdz, sigma, gd)
-    if es is o.env_shade:
+    cd, cs = impl.bilateral_bwd(nn, zdz, sigma, gd), impl.bilateral_bwd(nn, zdz, sigma, gd)
+    if impl is o:
         g = es(*args, n_samples_x=N, rnd_seed=seed, vis_mode="bvh", grads=(cd, cs), parallel_bwd=True)
     else:
         g = es(*args, n_samples_x=N, rnd_seed=seed, vis_mode="bvh", grads=(cd, cs))
@@ -357,9 +357,10 @@ def host_cores():
 
 
 REF_ARM_NOTE = {
-    "reference": "env_shade forward + backward = the reference's own raygen program (render/optixutils/c_src/envsampling/kernel.cu with bsdf.h, "
-                 "math_utils.h) compiled for the host cores (oracle/_ref, OpenMP over pixels), shadow rays answered by the oracle's LBVH (OptiX itself "
-                 "is closed source and needs an RT driver); denoiser / shading normal / update_pdf / LBVH build = oracle C port",
+    "reference": "env_shade forward + backward and the bilateral denoiser forward + backward = the reference's own kernels (render/optixutils/c_src/"
+                 "envsampling/kernel.cu with bsdf.h, math_utils.h; denoising.cu) compiled for the host cores (oracle/_ref, OpenMP over pixels), shadow "
+                 "rays answered by the oracle's LBVH (OptiX itself is closed source and needs an RT driver); shading normal / update_pdf / LBVH build "
+                 "= oracle C port",
     "port": "CPU oracle port of kernel.cu/denoising.cu/normal.cu (oracle/_ref not available on this machine; OptiX needs libnvoptix + RT driver)",
 }
 

@@ -58,24 +58,32 @@ def build(force=False):
 # oracle/_ref: the UNMODIFIED reference raygen program compiled for the host (oracle/ref_shim/), only where /root/reference exists
 # ------------------------------------------------------------------------------------------------
 REF_KERNEL = "/root/reference/render/optixutils/c_src/envsampling/kernel.cu"
+REF_DENOISE = "/root/reference/render/optixutils/c_src/denoising.cu"
+REF_RU_BSDF = "/root/reference/render/renderutils/c_src/bsdf.cu"
+REF_RU_NORMAL = "/root/reference/render/renderutils/c_src/normal.cu"
 _REF_DIR = os.path.join(_HERE, "_ref")
 _REF_LIB = os.path.join(_REF_DIR, "libref_envshade.so")
+_REF_LIB_DN = os.path.join(_REF_DIR, "libref_denoise.so")
+_REF_LIB_RU = os.path.join(_REF_DIR, "libref_renderutils.so")
 _SHIM = os.path.join(_HERE, "ref_shim")
 
 
 def build_ref(force=False):
-    """g++ on the reference's own kernel.cu (and the headers it includes) where it lies, through the host shim.  Returns the library path,
-    or None when the reference tree is not present (GPU box) and no prebuilt library travelled with the snapshot."""
+    """g++ on the reference's own kernel.cu / denoising.cu (and the headers they include) where they lie, through the host shims.  Returns
+    the env_shade library path, or None when the reference tree is not present (GPU box) and no prebuilt library travelled with the snapshot."""
     if not os.path.exists(REF_KERNEL):
-        return _REF_LIB if os.path.exists(_REF_LIB) else None
-    srcs = [os.path.join(_SHIM, "ref_env_shade.cpp"), os.path.join(_SHIM, "optix.h"), REF_KERNEL]
-    if not force and os.path.exists(_REF_LIB) and all(os.path.getmtime(_REF_LIB) >= os.path.getmtime(s) for s in srcs):
-        return _REF_LIB
-    os.makedirs(_REF_DIR, exist_ok=True)
+        return _REF_LIB if all(os.path.exists(l) for l in (_REF_LIB, _REF_LIB_DN, _REF_LIB_RU)) else None
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-w", "-I" + cuda_inc, "-I" + _SHIM,
-           "-I" + os.path.dirname(REF_KERNEL), '-DREF_KERNEL="%s"' % REF_KERNEL, srcs[0], "-o", _REF_LIB]
-    subprocess.run(cmd, check=True)
+    jobs = [(_REF_LIB, "ref_env_shade.cpp", {"REF_KERNEL": REF_KERNEL}), (_REF_LIB_DN, "ref_denoise.cpp", {"REF_DENOISE": REF_DENOISE}),
+            (_REF_LIB_RU, "ref_renderutils.cpp", {"REF_RU_BSDF": REF_RU_BSDF, "REF_RU_NORMAL": REF_RU_NORMAL})]
+    for out, shim, macros in jobs:
+        srcs = [os.path.join(_SHIM, shim), os.path.join(_SHIM, "optix.h")] + list(macros.values())
+        if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
+            continue
+        os.makedirs(_REF_DIR, exist_ok=True)
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-w", "-I" + cuda_inc, "-I" + _SHIM]
+        cmd += ["-I" + d for d in sorted({os.path.dirname(v) for v in macros.values()})] + ['-D%s="%s"' % kv for kv in macros.items()]
+        subprocess.run(cmd + [srcs[0], "-o", out], check=True)
     return _REF_LIB
 
 
@@ -92,6 +100,61 @@ class Reference:
         self.lib = C.CDLL(path)
         self.lib.ref_set_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         self.lib.ref_env_shade.argtypes = [C.c_int] * 7 + [C.c_uint, C.c_uint, C.c_float, C.c_int] + [C.c_void_p] * 21
+        self.dn = C.CDLL(_REF_LIB_DN)
+        self.dn.ref_bilateral_fwd.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float] + [C.c_void_p] * 4
+        self.dn.ref_bilateral_bwd.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float] + [C.c_void_p] * 5
+
+        self.ru = C.CDLL(_REF_LIB_RU)
+
+        class _Desc(C.Structure):
+            _fields_ = [("val", C.c_void_p), ("d_val", C.c_void_p), ("dims", C.c_int * 4)]
+        self._Desc = _Desc
+        self.ru.ref_ru_run.argtypes = [C.c_char_p, C.c_int, C.POINTER(_Desc), C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int]
+
+    def renderutils(self, kernel, ins, out_channels=None, dout=None, f0=0.0, i0=0, i1=0):
+        """Run one per-pixel kernel of render/renderutils/c_src/{bsdf,normal}.cu.  `kernel`: lambert|frostbite|fresnel|ndf|lambda|masking|
+        specular|bsdf|psn + _fwd / _bwd.  ins: [N|1, H|1, W|1, C] arrays in the order of the kernel's parameter struct.  Forward returns
+        out [N,H,W,out_channels]; backward (dout = upstream gradient) returns one full-grid gradient per input, as the plugin does
+        before the Python side sums broadcast dimensions (renderutils/ops.py)."""
+        ins = [np.ascontiguousarray(a, np.float32) for a in ins]
+        grid = np.broadcast_shapes(*[a.shape[:3] for a in ins])
+        N, H, W = grid
+        bwd = dout is not None
+        keep, descs = [], (self._Desc * (len(ins) + 1))()
+        grads = []
+        for i, a in enumerate(ins):
+            descs[i].val = a.ctypes.data
+            if bwd:
+                g = np.zeros((N, H, W, a.shape[3]), np.float32); grads.append(g); descs[i].d_val = g.ctypes.data
+            for k in range(4):
+                descs[i].dims[k] = a.shape[k]
+        out = np.ascontiguousarray(dout, np.float32) if bwd else np.zeros((N, H, W, out_channels), np.float32)
+        descs[len(ins)].val = out.ctypes.data
+        for k, v in enumerate(out.shape):
+            descs[len(ins)].dims[k] = v
+        rc = self.ru.ref_ru_run(kernel.encode(), len(ins) + 1, descs, W, H, N, float(f0), int(i0), int(i1))
+        if rc != 0:
+            raise ValueError("ref_ru_run(%s): %s" % (kernel, {1: "unknown kernel", 2: "wrong tensor count"}.get(rc, rc)))
+        return grads if bwd else out
+
+    def bilateral_fwd(self, col, nrm, zdz, sigma):
+        """bilateral_denoiser_fwd_kernel (denoising.cu:14-72): -> [B,H,W,4] (rgb weighted sum, weight)."""
+        f = lambda a: np.ascontiguousarray(a, np.float32)
+        col, nrm, zdz = f(col), f(nrm), f(zdz)
+        B, H, W = col.shape[:3]
+        out = np.zeros((B, H, W, 4), np.float32)
+        self.dn.ref_bilateral_fwd(B, H, W, float(sigma), col.ctypes.data, nrm.ctypes.data, zdz.ctypes.data, out.ctypes.data)
+        return out
+
+    def bilateral_bwd(self, nrm, zdz, sigma, out_grad, col=None):
+        """bilateral_denoiser_bwd_kernel (denoising.cu:74-130): out_grad [B,H,W,4] -> col_grad [B,H,W,3]."""
+        f = lambda a: np.ascontiguousarray(a, np.float32)
+        nrm, zdz, og = f(nrm), f(zdz), f(out_grad)
+        B, H, W = nrm.shape[:3]
+        col = np.zeros((B, H, W, 3), np.float32) if col is None else f(col)
+        cg = np.zeros((B, H, W, 3), np.float32)
+        self.dn.ref_bilateral_bwd(B, H, W, float(sigma), col.ctypes.data, nrm.ctypes.data, zdz.ctypes.data, og.ctypes.data, cg.ctypes.data)
+        return cg
 
     def env_shade(self, scene, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms, BSDF="pbr", n_samples_x=8,
                   rnd_seed=0, shadow_scale=1.0, grads=None, vis_mode="brute"):

@@ -31,6 +31,8 @@
 #endif
 
 // ---- CUDA's mixed-precision min / max overloads and the device-only names the source relies on ----
+// CUDA resolves abs(float) to the float overload; make the host do the same (plain ::abs would be int abs(int))
+using std::abs;
 static inline float max(float a, float b) { return fmaxf(a, b); }
 static inline float min(float a, float b) { return fminf(a, b); }
 static inline double max(double a, float b) { return fmax(a, (double)b); }
