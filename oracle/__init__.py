@@ -61,6 +61,8 @@ REF_KERNEL = "/root/reference/render/optixutils/c_src/envsampling/kernel.cu"
 REF_DENOISE = "/root/reference/render/optixutils/c_src/denoising.cu"
 REF_RU_BSDF = "/root/reference/render/renderutils/c_src/bsdf.cu"
 REF_RU_NORMAL = "/root/reference/render/renderutils/c_src/normal.cu"
+REF_RU_LOSS = "/root/reference/render/renderutils/c_src/loss.cu"
+REF_RU_MESH = "/root/reference/render/renderutils/c_src/mesh.cu"
 _REF_DIR = os.path.join(_HERE, "_ref")
 _REF_LIB = os.path.join(_REF_DIR, "libref_envshade.so")
 _REF_LIB_DN = os.path.join(_REF_DIR, "libref_denoise.so")
@@ -75,7 +77,7 @@ def build_ref(force=False):
         return _REF_LIB if all(os.path.exists(l) for l in (_REF_LIB, _REF_LIB_DN, _REF_LIB_RU)) else None
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     jobs = [(_REF_LIB, "ref_env_shade.cpp", {"REF_KERNEL": REF_KERNEL}), (_REF_LIB_DN, "ref_denoise.cpp", {"REF_DENOISE": REF_DENOISE}),
-            (_REF_LIB_RU, "ref_renderutils.cpp", {"REF_RU_BSDF": REF_RU_BSDF, "REF_RU_NORMAL": REF_RU_NORMAL})]
+            (_REF_LIB_RU, "ref_renderutils.cpp", {"REF_RU_BSDF": REF_RU_BSDF, "REF_RU_NORMAL": REF_RU_NORMAL, "REF_RU_LOSS": REF_RU_LOSS, "REF_RU_MESH": REF_RU_MESH})]
     for out, shim, macros in jobs:
         srcs = [os.path.join(_SHIM, shim), os.path.join(_SHIM, "optix.h")] + list(macros.values())
         if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
@@ -110,6 +112,37 @@ class Reference:
             _fields_ = [("val", C.c_void_p), ("d_val", C.c_void_p), ("dims", C.c_int * 4)]
         self._Desc = _Desc
         self.ru.ref_ru_run.argtypes = [C.c_char_p, C.c_int, C.POINTER(_Desc), C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int]
+
+    def image_loss(self, img, target, loss="l1", tonemapper="none", dout=None):
+        """imgLossFwdKernel / imgLossBwdKernel (loss.cu:105-227).  Forward -> the mean of the per-pixel loss, as renderutils/ops.py:494 returns
+        it; with dout (upstream gradient of that mean) -> (img_grad, target_grad)."""
+        li = {"l1": 0, "mse": 1, "relmse": 2, "smape": 3, "n2n": 4}[loss]
+        ti = 1 if tonemapper == "log_srgb" else 0
+        img = np.ascontiguousarray(img, np.float32); target = np.ascontiguousarray(target, np.float32)
+        n = img.shape[0] * img.shape[1] * img.shape[2]
+        if dout is None:
+            return float(self.renderutils("loss_fwd", [img, target], 1, i0=ti, i1=li).astype(np.float64).sum() / n)
+        g = np.full(img.shape[:3] + (1,), np.float32(dout) / np.float32(n), np.float32)
+        return self.renderutils("loss_bwd", [img, target], dout=g, i0=ti, i1=li)
+
+    def xfm(self, points, matrix, is_points=True, dout=None):
+        """xfmPointsFwdKernel / xfmPointsBwdKernel (mesh.cu:19-90).  points [B|1,V,3], matrix [B,4,4] -> [B,V,4|3]; with dout -> points gradient
+        on the full batch [B,V,3] (the Python side sums it for a broadcast input)."""
+        pts = np.ascontiguousarray(points, np.float32); mtx = np.ascontiguousarray(matrix, np.float32)
+        B, V = mtx.shape[0], pts.shape[1]
+        D = self._Desc
+        descs = (D * 3)()
+        out = np.zeros((B, V, 4 if is_points else 3), np.float32) if dout is None else np.ascontiguousarray(dout, np.float32)
+        grad = np.zeros((B, V, 3), np.float32)
+        for i, a in enumerate((pts, mtx, out)):
+            descs[i].val = a.ctypes.data
+            for k, v in enumerate(a.shape + (1,)):
+                descs[i].dims[k] = v
+        if dout is not None:
+            descs[0].d_val = grad.ctypes.data
+        rc = self.ru.ref_ru_run(b"xfm_bwd" if dout is not None else b"xfm_fwd", 3, descs, V, 1, B, 0.0, 1 if is_points else 0, 0)
+        assert rc == 0
+        return grad if dout is not None else out
 
     def renderutils(self, kernel, ins, out_channels=None, dout=None, f0=0.0, i0=0, i1=0):
         """Run one per-pixel kernel of render/renderutils/c_src/{bsdf,normal}.cu.  `kernel`: lambert|frostbite|fresnel|ndf|lambda|masking|

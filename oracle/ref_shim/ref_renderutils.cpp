@@ -1,7 +1,11 @@
-// ref_renderutils.cpp -- TEST INFRASTRUCTURE (oracle/_ref): compiles the UNMODIFIED per-pixel kernels of the reference's renderutils
-// plugin, render/renderutils/c_src/bsdf.cu (16 kernels) and normal.cu (2 kernels) with bsdf.h, normal.h, common.h, tensor.h, vec3f.h,
-// vec4f.h, for the host from where they lie under /root/reference, and runs them one "thread" per pixel.  Nothing of the reference is
-// copied; conventions as in ref_env_shade.cpp.  (loss.cu uses warp shuffles and mesh.cu shared memory + barriers: not driven here.)
+// ref_renderutils.cpp -- TEST INFRASTRUCTURE (oracle/_ref): compiles the UNMODIFIED kernels of the reference's renderutils plugin,
+// render/renderutils/c_src/bsdf.cu (16 kernels), normal.cu (2), loss.cu (2) and mesh.cu (2) with bsdf.h, normal.h, loss.h, mesh.h,
+// common.h, tensor.h, vec3f.h, vec4f.h, for the host from where they lie under /root/reference.  Nothing of the reference is copied;
+// conventions as in ref_env_shade.cpp.  The per-pixel kernels run one "thread" per pixel in 1x1x1 blocks.  loss.cu reduces over a warp
+// with __shfl_xor_sync: in a 1x1x1 block getWarpSize() is (1,1,1), the other 31 lanes hold 0, so the kernel writes the per-pixel loss
+// (the Python side sums the partial tensor either way, renderutils/ops.py:494).  mesh.cu stages the matrix in __shared__ memory behind a
+// __syncthreads(): a block of 16 threads is run twice on one OS thread (first pass fills the staging array, second pass reads it; the
+// outputs are plain stores, so the second pass overwrites the first).
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -41,9 +45,16 @@ static inline unsigned int min(unsigned int a, unsigned int b) { return a < b ? 
 
 static thread_local uint3 blockIdx, threadIdx;
 static thread_local dim3 blockDim;
+#define __shared__ static thread_local
+static inline void __syncthreads() {}
+static inline float __shfl_xor_sync(unsigned, float, int) { return 0.0f; }          // lanes outside the 1-thread block contribute nothing
+dim3 getLaunchBlockSize(int, int, dim3) { return dim3(1, 1, 1); }                     // declared (not defined) by common.h
+dim3 getLaunchGridSize(dim3, dim3 d) { return d; }
 
 #include REF_RU_BSDF
 #include REF_RU_NORMAL
+#include REF_RU_LOSS
+#include REF_RU_MESH
 
 namespace {
 
@@ -104,6 +115,34 @@ extern "C" int ref_ru_run(const char *name, int nt, const Desc *d, int gx, int g
         if (nt != 7) return 2;
         PbrBSDF p; fill(p, nt, d, gx, gy, gz); p.min_roughness = f0; p.BSDF = i0;
         launch(k == "bsdf_fwd" ? pbrBSDFFwdKernel : pbrBSDFBwdKernel, p);
+        return 0;
+    }
+    if (k == "loss_fwd" || k == "loss_bwd") {        // tensors: img, target, out (fwd: per-pixel loss [N,H,W,1]; bwd: its upstream gradient)
+        if (nt != 3) return 2;
+        LossKernelParams p; fill(p, nt, d, gx, gy, gz); p.tonemapper = (TonemapperType)i0; p.loss = (LossType)i1;
+        launch(k == "loss_fwd" ? imgLossFwdKernel : imgLossBwdKernel, p);
+        return 0;
+    }
+    if (k == "xfm_fwd" || k == "xfm_bwd") {          // tensors: points [B|1,V,3(,1)], matrix [B,4,4(,1)], out [B,V,4|3(,1)]; gx = V, gz = B
+        if (nt != 3) return 2;
+        XfmKernelParams p; std::memset((void *)&p, 0, sizeof(p));
+        Tensor *t[3] = {&p.points, &p.matrix, &p.out};
+        for (int i = 0; i < 3; ++i) {
+            t[i]->val = d[i].val; t[i]->d_val = d[i].d_val; t[i]->fp16 = false;
+            int st = 1;
+            for (int q = 3; q >= 0; --q) { t[i]->dims[q] = d[i].dims[q]; t[i]->strides[q] = st; st *= d[i].dims[q]; }
+            t[i]->_dims[0] = gz; t[i]->_dims[1] = gx; t[i]->_dims[2] = d[i].dims[2]; t[i]->_dims[3] = 1;        // the 3-D branch of make_cuda_tensor, torch_bindings.cpp:121
+        }
+        p.isPoints = i0 != 0; p.gridSize = dim3(gx, 1, gz);
+        const int nb = (gx + 15) / 16;
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int z = 0; z < gz; ++z)
+            for (int b = 0; b < nb; ++b)
+                for (int pass = 0; pass < 2; ++pass)
+                    for (int tx = 0; tx < 16; ++tx) {
+                        blockDim = dim3(16, 1, 1); threadIdx = make_uint3((unsigned)tx, 0, 0); blockIdx = make_uint3((unsigned)b, 0, (unsigned)z);
+                        if (k == "xfm_fwd") xfmPointsFwdKernel(p); else xfmPointsBwdKernel(p);
+                    }
         return 0;
     }
     if (k == "psn_fwd" || k == "psn_bwd") {
