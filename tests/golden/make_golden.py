@@ -152,3 +152,32 @@ def make_update_pdf():
 
 if __name__ == "__main__":
     make_update_pdf()
+
+
+def make_env_shade():
+    """Rows a1-a8: outputs of the reference's OWN raygen program (kernel.cu, compiled unmodified for the host by oracle/ref_shim ->
+    oracle/_ref) on a small scene, frozen with their inputs, so that the pin also holds where oracle/_ref cannot be loaded.  Shadow
+    rays are answered by the oracle's brute-force predicate (the OptiX runtime is closed source)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(OUT), ""))          # tests/
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))           # repo root
+    from common import make_case, oracle
+    from oracle import Reference
+    o = oracle()
+    ref = Reference(o)
+    for tag, bsdf, N, shadow in (("pbr", "pbr", 4, 1.0), ("diffuse", "diffuse", 3, 0.5)):
+        c = make_case(res=14, B=2, N=N, level=1, light_hw=(16, 32), seed=7, perm_rows=64)
+        args = (c["scene"], c["mask"], c["ro"], c["pos"], c["nrm"], c["view"], c["kd"], c["ks"], c["light"], c["pdf"], c["rows"], c["cols"], c["perms"])
+        kw = dict(BSDF=bsdf, n_samples_x=N, rnd_seed=5, shadow_scale=shadow)
+        d, s = ref.env_shade(*args, **kw)
+        g = np.random.default_rng(2)
+        gd = g.uniform(size=d.shape).astype(np.float32); gs = g.uniform(size=d.shape).astype(np.float32)
+        grads = ref.env_shade(*args, grads=(gd, gs), **kw)
+        out = {k: c[k] for k in ("verts", "tris", "mask", "ro", "pos", "nrm", "view", "kd", "ks", "light", "pdf", "rows", "cols", "perms")}
+        out.update(diff=d, spec=s, diff_grad=gd, spec_grad=gs, pos_grad=grads[0], nrm_grad=grads[1], kd_grad=grads[2], ks_grad=grads[3],
+                   light_grad=grads[4], n_samples_x=np.int32(N), rnd_seed=np.int32(5), shadow_scale=np.float32(shadow))
+        np.savez_compressed(os.path.join(OUT, "ref_env_shade_%s.npz" % tag), **out)
+        print("wrote ref_env_shade_" + tag, d.shape, float(d.mean()))
+
+
+if __name__ == "__main__":
+    make_env_shade()
