@@ -226,8 +226,9 @@ class GpuWorkload:
         return loss
 
 
-def time_env_kernels(w, reps=5):
-    """CUDA-event time of the fused env_shade forward and backward launches alone (stream = torch current stream)."""
+def time_env_kernels(w, reps=20, warm=5):
+    """CUDA-event time of the fused env_shade forward and backward launches alone (stream = torch current stream): median of `reps`
+    after `warm` untimed launches (median of >= 20 after 5 warm-ups); each launch draws a new seed, i.e. new rays."""
     import torch
     import nvdiffrecmc_b200.renderutils as ru
     ou, gb, wl = w.ou, w.gb, w.wl
@@ -237,7 +238,7 @@ def time_env_kernels(w, reps=5):
         ro = gb["pos"] + nrm0 * 0.001
         kd0 = w.kd_tex[gb["texel"]].detach(); ks0 = w.ks_tex[gb["texel"]].detach()
     fw, bw = [], []
-    for r in range(reps + 2):
+    for r in range(reps + warm):
         nrm = nrm0.clone().requires_grad_(True); kd = kd0.clone().requires_grad_(True); ks = ks0.clone().requires_grad_(True)
         light = w.lgt.base.detach().clone().requires_grad_(True)
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -250,7 +251,7 @@ def time_env_kernels(w, reps=5):
         torch.autograd.backward([d, s], [gd, gs])
         e[3].record()
         torch.cuda.synchronize()
-        if r >= 2:
+        if r >= warm:
             fw.append(e[0].elapsed_time(e[1])); bw.append(e[2].elapsed_time(e[3]))
     return float(np.median(fw)), float(np.median(bw))
 

@@ -14,6 +14,6 @@ w = bench.GpuWorkload(wl, 0, 1, dev)
 if "KB_SHADOW" in os.environ:            # e.g. KB_SHADOW=0: skip the trace phase entirely (sampling + shading cost alone)
     _orig = w.ou.optix_env_shade
     w.ou.optix_env_shade = lambda *a, **k: _orig(*a, shadow_scale=float(os.environ["KB_SHADOW"]), **k)
-f, b = bench.time_env_kernels(w, reps=5)
+f, b = bench.time_env_kernels(w, reps=5, warm=2)
 print(json.dumps({"lib": os.environ.get("MCS_LIB", "default"), "views": wl["views_per_gpu"], "fwd_ms": round(f, 3), "bwd_ms": round(b, 3),
                   "fwd_mrays": round(w.rays_per_pass / f / 1e3, 1), "bwd_mrays": round(w.rays_per_pass / b / 1e3, 1)}))
