@@ -13,8 +13,8 @@
 //       G  generate: every warp draws the 2N^2 samples of its pixel (exact path, all lanes); rays that can contribute
 //          (n.wi > 0) are ballot-compacted into the warp's segment of a block-wide shared-memory queue (direction, env
 //          texel, MIS weight);
-//       T  trace: all warps drain the queue together -- own segment first, then work stealing -- with one binary-BVH node
-//          step per lane per iteration, leaf tests deferred to full-warp batches, dynamic ray fetch;  one bit per ray;
+//       T  trace: all warps drain the queue together -- own segment first, then work stealing -- with one 4-wide quantised
+//          BVH node step per lane per iteration (v6), leaf tests deferred to full-warp batches, dynamic ray fetch; one bit per ray;
 //       E  evaluate: each warp compacts the surviving rays (V != 0) of its pixel and only those evaluate the BSDF (forward)
 //          or its adjoint + the env-map gradient scatter (backward); warp-shuffle reduction, one writer per pixel.
 //     The reference runs one thread per pixel and loops 2*N^2 samples serially with an optixTrace per sample.
@@ -28,10 +28,12 @@
 //     about half of the light-sampled rays.
 //   * Sampling decisions use exact.cuh arithmetic (bit-identical texel / direction / lobe choice vs
 //     the oracle); BSDF evaluation, pdfs and adjoints use fast FMA math (bsdf.cuh).
-//   * Backward replays the same random stream, evaluates the adjoint BSDF only for visible rays,
-//     reduces the per-pixel gradients in registers/shuffles (single writer per pixel like the
-//     reference's `+=`, kernel.cu:442-456) and scatters the env-map gradient with float atomics
-//     (kernel.cu:203-211), skipping zero contributions.
+//   * Backward: when forward and backward share the seed (the reference's training loop always does) the forward records the
+//     rays it evaluated (direction, MIS weight, texel, occluded flag) and env_shade_replay_kernel walks that record: adjoint BSDF +
+//     gradient scatter only, no sampling, no traversal.  Otherwise env_shade_kernel<1> replays the random stream and re-traces
+//     like the reference.  Either way the per-pixel gradients are reduced in registers / shuffles (single writer per pixel like the
+//     reference's `+=`, kernel.cu:442-456) and the env-map gradient is scattered with float atomics (kernel.cu:203-211),
+//     skipping zero contributions.
 #include "bsdf.cuh"
 #include "bvh_traverse.cuh"
 #include "ctx.h"
