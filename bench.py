@@ -366,6 +366,23 @@ REF_ARM_NOTE = {
 }
 
 
+def physical_limiter(path=None):
+    """What the committed ncu capture of the dominant kernel says actually bounds it (the contract's HBM roofline counts logical bytes that
+    this L1/L2-resident workload never moves): issue-slot utilisation, lanes per instruction, L1 data-pipe and DRAM utilisation."""
+    path = path or os.path.join(ROOT, "profiles", "r01_v6_envshade_summary.json")
+    try:
+        with open(path) as f:
+            k = json.load(f)["kernels"][0]
+        num = lambda key: float(str(k[key]).split()[0])
+        return {"limiter": "instruction issue", "source": os.path.relpath(path, ROOT),
+                "issue_active_pct_of_peak": round(num("smsp__issue_active.avg.pct_of_peak_sustained_active"), 1),
+                "active_lanes_per_instruction": round(num("smsp__thread_inst_executed_per_inst_executed.ratio"), 1),
+                "l1_data_pipe_pct_of_peak": round(num("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"), 1),
+                "dram_pct_of_peak": round(num("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"), 2)}
+    except Exception:
+        return None
+
+
 def run_reference(args, wl):
     """--impl reference: the reference's algorithm on the host CPUs (oracle port; OptiX cannot be built/run here)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -580,7 +597,7 @@ def main():
                          "algorithmic_bytes_per_ray": round(a_bwd, 1), "mrays_per_s": round(w.rays_per_pass / k_bwd_ms / 1e3, 1)},
             "note": "achieved = LOGICAL bytes (SURVEY 8d model: every CDF probe, texel, canonical-LBVH node and triangle counted as a memory access) "
                     "x logical rays / kernel time; all tables of this mesh are L1/L2 resident so the physical DRAM traffic (`traffic`) is ~%.1f B/ray "
-                    "and the kernel is instruction-issue / latency bound (profiles/r01_v4_*). Rays with n.wi<=0 (exactly zero contribution) are "
+                    "and the kernel is instruction-issue bound (`physical_limiter`, profiles/r01_v6_*). Rays with n.wi<=0 (exactly zero contribution) are "
                     "counted as the reference counts them but not traced: see traced_fraction / frac_traced_rays_only. The backward kernel "
                     "replays the forward hit record instead of tracing." % (88.0 / (2 * N * N) + 4)}
     prof = os.path.join(ROOT, "profiles", "r01_env_shade_fwd_traffic.json")
@@ -590,6 +607,7 @@ def main():
                 roof["traffic"] = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             pass
+    roof["physical_limiter"] = physical_limiter()
 
     cpu = None
     if not args.no_cpu_baseline:

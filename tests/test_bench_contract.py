@@ -33,3 +33,11 @@ def test_non_zero_ranks_of_the_reference_arm_stay_silent():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, env=env, timeout=120, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_physical_limiter_is_read_from_the_committed_capture():
+    import bench
+    p = bench.physical_limiter()
+    assert p is not None and p["limiter"] == "instruction issue" and p["source"].startswith("profiles/")
+    assert 50 < p["issue_active_pct_of_peak"] <= 100 and 1 <= p["active_lanes_per_instruction"] <= 32 and p["dram_pct_of_peak"] < 50
+    assert bench.physical_limiter("/nonexistent.json") is None          # a missing capture never breaks the bench line
