@@ -100,3 +100,17 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "mcoracle" not in src.replace("oracle/mcoracle.c", ""), f    # comments may cite the oracle file, code may not include it
+
+
+def test_docs_are_sane():
+    """Guard against a runaway search-and-replace (it happened once: DESIGN.md grew to 22 MB): the documents the review reads are small,
+    start with their title and name every §8 row."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name, title in (("DESIGN.md", "# DESIGN"), ("INTEGRATION.md", "# INTEGRATION"), ("README.md", "# b200-mcshade")):
+        p = os.path.join(root, name)
+        assert os.path.getsize(p) < 200 * 1024, name
+        assert open(p).read(200).startswith(title), name
+    d = open(os.path.join(root, "DESIGN.md")).read()
+    for needle in ("SURVEY §8 a/b", "Oracle and parity", "Data layout in HBM", "Kernels", "Measurement", "Multi-GPU", "Out of scope", "oracle/_ref"):
+        assert needle in d, needle
