@@ -102,6 +102,7 @@ class Reference:
         self.lib = C.CDLL(path)
         self.lib.ref_set_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         self.lib.ref_env_shade.argtypes = [C.c_int] * 7 + [C.c_uint, C.c_uint, C.c_float, C.c_int] + [C.c_void_p] * 21
+        self.lib.ref_set_ray_log.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         self.dn = C.CDLL(_REF_LIB_DN)
         self.dn.ref_bilateral_fwd.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float] + [C.c_void_p] * 4
         self.dn.ref_bilateral_bwd.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float] + [C.c_void_p] * 5
@@ -190,8 +191,10 @@ class Reference:
         return cg
 
     def env_shade(self, scene, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms, BSDF="pbr", n_samples_x=8,
-                  rnd_seed=0, shadow_scale=1.0, grads=None, vis_mode="brute"):
-        """Forward -> (diff, spec); with grads=(diff_grad, spec_grad) -> (pos_grad, nrm_grad, kd_grad, ks_grad, light_grad)."""
+                  rnd_seed=0, shadow_scale=1.0, grads=None, vis_mode="brute", ray_log=False):
+        """Forward -> (diff, spec); with grads=(diff_grad, spec_grad) -> (pos_grad, nrm_grad, kd_grad, ks_grad, light_grad).
+        ray_log=True (forward only) appends the directions of the shadow rays the reference traced, [B,H,W,2*n^2,3] in sample-slot
+        order (NaN where the pixel is masked)."""
         f = lambda a: np.ascontiguousarray(a, np.float32)
         mask, ro, gb_pos, gb_normal, gb_kd, gb_ks = [f(a) for a in (mask, ro, gb_pos, gb_normal, gb_kd, gb_ks)]
         B, H, W = mask.shape
@@ -207,9 +210,17 @@ class Reference:
         occ = C.cast(self.orc.lib.orc_occluded1, C.c_void_p)
         self.lib.ref_set_visibility(occ, scene.h, {"brute": 0, "bvh": 1}[vis_mode])
         p = lambda a: a.ctypes.data
+        S2 = 2 * n_samples_x * n_samples_x
+        if ray_log:
+            dirs = np.full((B, H, W, S2, 3), np.nan, np.float32); cnt = np.zeros((B, H, W), np.int32)
+            self.lib.ref_set_ray_log(p(dirs), p(cnt), S2)
         self.lib.ref_env_shade(B, H, W, Hl, Wl, perms.shape[0], n_samples_x, BSDF_MODES.index(BSDF), int(rnd_seed) & 0xFFFFFFFF, float(shadow_scale),
                                0 if grads is None else 1, p(mask), p(ro), p(gb_pos), p(gb_normal), p(view), p(gb_kd), p(gb_ks), p(light), p(pdf), p(rows),
                                p(cols), p(perms), p(diff), p(spec), p(dg), p(sg), p(pg), p(ng), p(kg), p(sgd), p(lg))
+        if ray_log:
+            self.lib.ref_set_ray_log(None, None, 0)
+            assert int(cnt.max()) <= S2
+            return diff, spec, dirs
         return (diff, spec) if grads is None else (pg, ng, kg, sgd, lg)
 
 
@@ -402,6 +413,13 @@ class Oracle:
                          [3] * 6, [int(two_sided_shading), int(opengl)], [3] * 6, dout=dout, dout_ch=3)
 
     # ------------------------------------------------------------------ light pdf / cdf
+    def dirs_to_texels(self, dirs, Hl, Wl):
+        """Env texel ((y << 16) | x) of each direction, computed exactly as env_shade records it."""
+        d = np.ascontiguousarray(dirs, self.dt).reshape(-1, 3)
+        out = np.zeros(d.shape[0], np.int32)
+        self.lib.orc_dirs_to_texels(C.c_int(d.shape[0]), C.c_int(Hl), C.c_int(Wl), C.c_void_p(d.ctypes.data), C.c_void_p(out.ctypes.data))
+        return out.reshape(np.asarray(dirs).shape[:-1])
+
     def update_pdf(self, base):
         base = self._a(base); H, W = base.shape[:2]
         pdf = np.zeros((H, W), self.dt); rows = np.zeros(H, self.dt); cols = np.zeros((H, W), self.dt)

@@ -15,6 +15,7 @@ struct RefShimState {                      /* per-thread launch state */
 };
 extern thread_local RefShimState g_shim;
 bool ref_shim_occluded(float3 o, float3 d, float tmin, float tmax);      /* defined in ref_env_shade.cpp */
+void ref_shim_log_ray(float3 o, float3 d);                              /* optional per-pixel ray log (test hook) */
 extern "C" void __miss__ms();
 
 static inline uint3 optixGetLaunchIndex() { return g_shim.idx; }
@@ -24,6 +25,7 @@ static inline void optixTrace(OptixTraversableHandle, float3 origin, float3 dir,
                               unsigned int, unsigned int, unsigned int, unsigned int &p0)
 {
     g_shim.payload0 = p0;
+    ref_shim_log_ray(origin, dir);
     if (!ref_shim_occluded(origin, dir, tmin, tmax)) __miss__ms();      /* any-hit and closest-hit programs are disabled by the ray flags */
     p0 = g_shim.payload0;
 }

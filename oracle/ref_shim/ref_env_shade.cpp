@@ -74,6 +74,18 @@ bool ref_shim_occluded(float3 o, float3 d, float, float)
     return g_occ(g_scene, g_vis_mode, ro, rd) != 0;
 }
 
+// ---- optional ray log: direction of every optixTrace call, per pixel in call order (= sample slot order: light i, BSDF i, ...) ----
+static float *g_log = nullptr;
+static int *g_log_cnt = nullptr;
+static int g_log_cap = 0;
+void ref_shim_log_ray(float3, float3 d)
+{
+    if (!g_log) return;
+    const size_t pix = ((size_t)g_shim.idx.z * g_shim.dim.y + g_shim.idx.y) * g_shim.dim.x + g_shim.idx.x;
+    const int k = g_log_cnt[pix]++;                                    // one OS thread per pixel: no race
+    if (k < g_log_cap) { float *o = g_log + (pix * g_log_cap + k) * 3; o[0] = d.x; o[1] = d.y; o[2] = d.z; }
+}
+
 namespace {
 template <int N> struct Raw { void *p; int32_t sizes[N]; int32_t strides[N]; };
 template <int N, class A> void fill(A &dst, const void *p, const int32_t *sizes)
@@ -87,6 +99,8 @@ template <int N, class A> void fill(A &dst, const void *p, const int32_t *sizes)
 }  // namespace
 
 extern "C" {
+
+void ref_set_ray_log(float *dirs, int *counts, int cap) { g_log = dirs; g_log_cnt = counts; g_log_cap = cap; }
 
 void ref_set_visibility(void *fn, const void *scene, int mode) { g_occ = (ref_occ_fn)fn; g_scene = scene; g_vis_mode = mode; }
 
