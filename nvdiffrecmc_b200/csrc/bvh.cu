@@ -341,7 +341,8 @@ int mcs_ctx_destroy(mcs_ctx *c)
 {
     if (!c) return 0;
     DevBuf *bufs[] = {&c->bounds, &c->tlo, &c->thi, &c->keys, &c->keys_alt, &c->vals, &c->vals_alt, &c->left, &c->right, &c->parent,
-                      &c->lo, &c->hi, &c->flags, &c->range, &c->sort_tmp, &c->nodes, &c->tris, &c->nodesq4, &c->qgrid, &c->lcg_skip, &c->light_grad4, &c->mtx_inv};
+                      &c->lo, &c->hi, &c->flags, &c->range, &c->sort_tmp, &c->nodes, &c->tris, &c->nodesq4, &c->qgrid, &c->lcg_skip[0], &c->lcg_skip[1], &c->lcg_skip[2], &c->lcg_skip[3],
+                      &c->counters, &c->mtx_inv};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     delete c;

@@ -6,6 +6,9 @@
 #pragma once
 #include "common.cuh"
 
+#define MCS_SKIP_TABLES 4
+#define MCS_COUNTER_RING 64
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -30,9 +33,12 @@ struct mcs_ctx {
     DevBuf nodesq4;              // [max(T-1,1)] x 4 uint4: 4-wide quantised view (the <= 4 grandchildren of binary node i), 16-bit boxes on a scene-wide grid
     DevBuf qgrid;                // 6 floats: grid origin xyz, cell size xyz
     // ---- env_shade support ----
-    DevBuf lcg_skip;             // [5*N*N+3] x uint2 (mul, add) LCG jump-ahead table for n_samples_x = skip_N
-    int skip_N = 0;
-    DevBuf light_grad4;          // scratch
+    DevBuf lcg_skip[MCS_SKIP_TABLES];   // [5*N*N+3] x uint2 (mul, add) LCG jump-ahead tables, one per cached n_samples_x
+    int skip_N[MCS_SKIP_TABLES] = {0, 0, 0, 0};
+    int n_skip = 0;
+    unsigned skip_evict = 0;
+    DevBuf counters;             // ring of 64-byte slots: per-launch work-claim counters of the persistent env_shade grid
+    unsigned counter_next = 0;
     DevBuf mtx_inv;              // [B,4,4] inverse clip matrices of the last mcs_rasterize call
 };
 

@@ -904,21 +904,35 @@ __global__ void __launch_bounds__(256, MCS_REPLAY_MINB) env_shade_replay_kernel(
     }
 }
 
-static int ensure_skip_table(mcs_ctx *c, int N, cudaStream_t s)
+// LCG jump-ahead table: entry k = (mul, add) with  state_after_k_steps = state * mul + add  (kernel.cu:33 is one step).  Built on the
+// device in one launch (thread k composes k steps by binary exponentiation of the affine map), cached per n_samples_x in the
+// context: no host copy, no host synchronisation, capturable in a CUDA graph, and alternating n_samples_x between calls
+// (training N=8 / validation N=32 style, train.py:303-305) does not rebuild anything.
+__global__ void k_skip_table(uint2 *__restrict__ tab, int n)
 {
-    if (c->skip_N == N && c->lcg_skip.p) return 0;
-    const int n = 5 * N * N + 3;
-    std::vector<uint2> h((size_t)n);
-    uint32_t m = 1u, a = 0u;
-    for (int k = 0; k < n; ++k) {
-        h[(size_t)k] = make_uint2(m, a);
-        a = a * 747796405u + 2891336453u;       // one more LCG step (kernel.cu:33)
-        m = m * 747796405u;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t m = 1u, a = 0u;                       // identity
+    uint32_t bm = 747796405u, ba = 2891336453u;    // one step
+    for (uint32_t e = (uint32_t)k; e; e >>= 1) {
+        if (e & 1u) { a = a * bm + ba; m = m * bm; }            // apply `b` after the steps composed so far
+        ba = ba * bm + ba; bm = bm * bm;                        // b <- b o b
     }
-    if (int e = mcs_buf_reserve(c->lcg_skip, sizeof(uint2) * (size_t)n + 16, s)) return e;
-    MCS_CUDA(cudaMemcpyAsync(c->lcg_skip.p, h.data(), sizeof(uint2) * (size_t)n, cudaMemcpyHostToDevice, s));
-    MCS_CUDA(cudaStreamSynchronize(s));        // one-off (table is cached per n_samples_x); keeps `h` alive
-    c->skip_N = N;
+    tab[k] = make_uint2(m, a);
+}
+
+static int ensure_skip_table(mcs_ctx *c, int N, cudaStream_t s, const uint2 **out)
+{
+    for (int i = 0; i < c->n_skip; ++i)
+        if (c->skip_N[i] == N) { *out = (const uint2 *)c->lcg_skip[i].p; return 0; }
+    const int slot = c->n_skip < MCS_SKIP_TABLES ? c->n_skip : (c->skip_evict++ % MCS_SKIP_TABLES);
+    const int n = 5 * N * N + 3;
+    if (int e = mcs_buf_reserve(c->lcg_skip[slot], sizeof(uint2) * (size_t)n + 16, s)) return e;
+    k_skip_table<<<(n + 255) / 256, 256, 0, s>>>((uint2 *)c->lcg_skip[slot].p, n);
+    MCS_LAUNCH_CHECK();
+    c->skip_N[slot] = N;
+    if (c->n_skip < MCS_SKIP_TABLES) ++c->n_skip;
+    *out = (const uint2 *)c->lcg_skip[slot].p;
     return 0;
 }
 
@@ -972,10 +986,11 @@ static int fill_params(mcs_ctx *ctx, EnvParams &p,
     p.m_rows = cdf_iters(p.Hl); p.m_cols = cdf_iters(p.Wl);
     p.bsdf = bsdf; p.seed = rnd_seed; p.batch_offset = batch_offset; p.shadow_scale = shadow_scale;
     p.bvh = BvhView{(const float4 *)ctx->nodes.p, (const float4 *)ctx->tris.p, (const float *)ctx->qgrid.p, (const uint4 *)ctx->nodesq4.p};
-    if (int e = ensure_skip_table(ctx, p.N, s)) return e;
-    p.skip = (const uint2 *)((const char *)ctx->lcg_skip.p);
-    if (int e = mcs_buf_reserve(ctx->light_grad4, 256, s)) return e;
-    p.chunk_counter = (unsigned int *)ctx->light_grad4.p;
+    if (int e = ensure_skip_table(ctx, p.N, s, &p.skip)) return e;
+    // work-claim counter of the persistent grid: one slot of a small ring PER LAUNCH, so launches of the same context that are in
+    // flight on different streams never share a counter
+    if (int e = mcs_buf_reserve(ctx->counters, MCS_COUNTER_RING * 64, s)) return e;
+    p.chunk_counter = (unsigned int *)((char *)ctx->counters.p + 64 * (size_t)(ctx->counter_next++ % MCS_COUNTER_RING));
     MCS_CUDA(cudaMemsetAsync(p.chunk_counter, 0, sizeof(unsigned int), s));
     return 0;
 }

@@ -17,9 +17,21 @@ _BSDF_MODES = ['pbr', 'diffuse', 'white']      # ops.py:136 -- order matters, it
 #           backward = adjoint BSDF + gradient scatter only (no sampling, no traversal);
 #   "bits": 1 visibility bit per sample (16 B/pixel); backward re-generates the samples but skips the traversal;
 #   None  : nothing; backward re-traces like the reference (torch_bindings.cpp:266-267).
-# "rays" falls back to "bits" when the record would exceed RAY_RECORD_MAX_BYTES.
+# "rays" falls back to "bits" when the record (B*H*W * 2N^2 * 20 B: 5.4 GB at 8 x 512^2, N = 8; 13.1 GB at 8 x 800^2) would exceed
+# RAY_RECORD_MAX_BYTES or RAY_RECORD_MAX_FREE_FRACTION of the device memory that is free at call time (nvdiffrast / tiny-cuda-nn
+# share the GPU in a real run; the reference itself stores nothing and re-traces).
 HIT_RECORD_REPLAY = "rays"
 RAY_RECORD_MAX_BYTES = 32 << 30
+RAY_RECORD_MAX_FREE_FRACTION = 0.5
+
+
+def _ray_record_fits(nbytes, device):
+    if nbytes > RAY_RECORD_MAX_BYTES:
+        return False
+    free, _total = torch.cuda.mem_get_info(device)
+    # memory cached by torch's allocator is reusable for the record even though the driver reports it as used
+    free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    return nbytes <= RAY_RECORD_MAX_FREE_FRACTION * free
 
 
 def _f32(t, name):
@@ -57,7 +69,7 @@ def optix_build_bvh(optix_ctx, verts, tris, rebuild):
     assert tris.shape[0] > 0, "Got empty training triangle mesh (unrecoverable discontinuity)"
     assert verts.shape[0] > 0, "Got empty training triangle mesh (unrecoverable discontinuity)"
     L.require_cuda(verts, tris)
-    v = _f32(verts, "verts").reshape(-1, 3).contiguous()
+    v = _f32(verts, "verts").detach().reshape(-1, 3).contiguous()      # detached: the context must not keep the caller's autograd graph alive
     if tris.dtype != torch.int32:
         raise RuntimeError("tris must be int32 (the reference's callers do .int(), geometry/dlmesh.py:50)")
     t = tris.reshape(-1, 3).contiguous()
@@ -111,7 +123,7 @@ class _optix_env_shade_func(torch.autograd.Function):
         mode = HIT_RECORD_REPLAY if (rnd_seed is not None and need_grad) else None
         if mode is True:
             mode = "bits"
-        if mode == "rays" and B * H * W * slots * 20 > RAY_RECORD_MAX_BYTES:
+        if mode == "rays" and not _ray_record_fits(B * H * W * (slots * 20 + 4), ro.device):
             mode = "bits"
         if mode == "rays":
             rec_cnt = torch.empty(B, H, W, dtype=torch.int32, device=ro.device)

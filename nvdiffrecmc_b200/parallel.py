@@ -26,9 +26,18 @@ def shard_views(global_batch, rank=None, world=None):
 class GradBucket:
     """Flat parameter + gradient storage: parameters are views into `flat`, their .grad are views into
     `flat_grad`, so `all_reduce_mean()` is a single collective on one contiguous buffer (no per-tensor launches,
-    no copies).  <= ~110 MB for the reference's largest configuration."""
+    no copies).  <= ~110 MB for the reference's largest configuration.
 
-    def __init__(self, shapes, device, dtype=torch.float32):
+    `GradBucket(shapes, device)` creates fresh leaf parameters; `GradBucket.adopt(params)` re-points EXISTING
+    parameters (the nn.Parameters the reference's modules own: light.base, the material textures, v_pos / sdf / deform,
+    train.py:340-356) into the flat storage in place, so the modules and the optimizer keep the very same tensor objects.
+
+    The aliasing `p.grad is a view of flat_grad` can be broken from outside: torch's `optimizer.zero_grad()` defaults to
+    set_to_none=True (the reference calls it every iteration, train.py:407-411), after which autograd allocates fresh
+    .grad tensors.  `all_reduce_mean()` therefore re-establishes the aliasing first (`sync_views`): a foreign .grad is
+    copied into its slice, a missing one zeroes its slice, and .grad is pointed back at the bucket -- never a stale reduce."""
+
+    def __init__(self, shapes, device, dtype=torch.float32, _params=None):
         self.shapes = [tuple(s) for s in shapes]
         sizes = [int(torch.Size(s).numel()) for s in self.shapes]
         self.offsets = [0]
@@ -38,15 +47,58 @@ class GradBucket:
         self.flat_grad = torch.zeros_like(self.flat)
         self.params = []
         for i, s in enumerate(self.shapes):
-            p = self.flat[self.offsets[i]:self.offsets[i + 1]].view(s).requires_grad_(True)
-            p.grad = self.flat_grad[self.offsets[i]:self.offsets[i + 1]].view(s)
+            if _params is None:
+                p = self.flat[self.offsets[i]:self.offsets[i + 1]].view(s).requires_grad_(True)
+            else:
+                p = _params[i]
+                with torch.no_grad():
+                    self.flat[self.offsets[i]:self.offsets[i + 1]].copy_(p.detach().reshape(-1))
+                    p.data = self.flat[self.offsets[i]:self.offsets[i + 1]].view(s)
+            p.grad = self._grad_view(i)
             self.params.append(p)
 
+    @classmethod
+    def adopt(cls, params):
+        """Bucket over existing leaf tensors / nn.Parameters (all on one device, one dtype): their storage moves into `flat`."""
+        params = [p for p in params if p.requires_grad]
+        if not params:
+            raise ValueError("GradBucket.adopt: no trainable parameters")
+        dev, dt = params[0].device, params[0].dtype
+        for p in params:
+            if p.device != dev or p.dtype != dt:
+                raise ValueError("GradBucket.adopt: parameters must share device and dtype (got %s/%s and %s/%s)" % (dev, dt, p.device, p.dtype))
+        return cls([p.shape for p in params], dev, dt, _params=params)
+
+    def _grad_view(self, i):
+        return self.flat_grad[self.offsets[i]:self.offsets[i + 1]].view(self.shapes[i])
+
     def zero_grad(self):
+        """Zero the bucket in one launch and keep every .grad aliased to it."""
         self.flat_grad.zero_()
+        for i, p in enumerate(self.params):
+            g = p.grad
+            if g is None or g.data_ptr() != self.flat_grad.data_ptr() + self.offsets[i] * self.flat_grad.element_size():
+                p.grad = self._grad_view(i)
+
+    def sync_views(self):
+        """Re-establish `p.grad aliases flat_grad` after something replaced or dropped the .grad tensors."""
+        esz = self.flat_grad.element_size()
+        base = self.flat_grad.data_ptr()
+        for i, p in enumerate(self.params):
+            g = p.grad
+            if g is not None and g.data_ptr() == base + self.offsets[i] * esz:
+                continue
+            view = self._grad_view(i)
+            with torch.no_grad():
+                if g is None:
+                    view.zero_()
+                else:
+                    view.copy_(g)
+            p.grad = view
 
     def all_reduce_mean(self, group=None):
-        """SUM all-reduce then divide by the world size; a no-op without an initialised process group."""
+        """SUM all-reduce then divide by the world size; a no-op (besides `sync_views`) without an initialised process group."""
+        self.sync_views()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
             self.flat_grad.div_(dist.get_world_size(group))
@@ -117,12 +169,19 @@ def shard_indices(n_items, global_batch, it, seed, rank=None, world=None):
 
 def hook_optimizer(optimizer, bucket, group=None):
     """Make `optimizer.step()` average the gradient bucket over the ranks first (ONE collective), so the reference's loop body
-    `total_loss.backward(); ...; optimizer.step()` (train.py:438-461) needs no edit.  Returns the optimizer."""
-    inner = optimizer.step
+    `optimizer.zero_grad(); ...; total_loss.backward(); ...; optimizer.step(); scheduler.step()` (train.py:407-461) needs no edit.
 
-    def step(*a, **k):
-        bucket.all_reduce_mean(group)
-        return inner(*a, **k)
+    * the all-reduce is a torch step PRE-HOOK (`Optimizer.register_step_pre_hook`), so `optimizer.step` stays the bound method that
+      `torch.optim.lr_scheduler.LambdaLR` wraps / inspects (train.py:349,353,356 build one scheduler per optimizer) -- hooking
+      before or after the scheduler is constructed both work;
+    * `optimizer.zero_grad()` is routed to `bucket.zero_grad()` (one memset, .grad stays aliased) regardless of `set_to_none`;
+      even without that, `all_reduce_mean` re-aliases foreign / missing .grad tensors (`GradBucket.sync_views`).
+    Returns the optimizer."""
+    import types
+    optimizer.register_step_pre_hook(lambda opt, args, kwargs: (bucket.all_reduce_mean(group), None)[1])
 
-    optimizer.step = step
+    def zero_grad(self, set_to_none=True):
+        bucket.zero_grad()
+
+    optimizer.zero_grad = types.MethodType(zero_grad, optimizer)
     return optimizer

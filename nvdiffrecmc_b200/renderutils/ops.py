@@ -238,6 +238,17 @@ def pbr_bsdf(kd, arm, pos, nrm, view_pos, light_pos, min_roughness=0.08, bsdf="l
 # ---------------------------------------------------------------------------------------------
 # Row f3 of SURVEY section 8: image loss and mesh transforms
 _LOSS_IDS = {"l1": 0, "mse": 1, "relmse": 2, "smape": 3, "n2n": 4}
+_TONEMAPPERS = {"none": 0, "log_srgb": 1}
+
+
+def _loss_ids(loss, tonemapper):
+    """The reference's CUDA path maps every unknown loss name to L1 (strToLoss, torch_bindings.cpp:727-737) -- which is how 'n2n'
+    silently became L1 there.  Unknown names raise here."""
+    if loss not in _LOSS_IDS:
+        raise ValueError("image_loss: unknown loss %r (expected one of %s)" % (loss, sorted(_LOSS_IDS)))
+    if tonemapper not in _TONEMAPPERS:
+        raise ValueError("image_loss: unknown tonemapper %r (expected one of %s)" % (tonemapper, sorted(_TONEMAPPERS)))
+    return _LOSS_IDS[loss], _TONEMAPPERS[tonemapper]
 
 
 class _image_loss_func(torch.autograd.Function):
@@ -250,7 +261,8 @@ class _image_loss_func(torch.autograd.Function):
         nparts = L.lib().mcs_image_loss_num_partials(N, H, W)
         out = torch.empty(nparts, dtype=torch.float32, device=img.device)
         a, b = L.nhwc(img), L.nhwc(target)
-        L.check(L.lib().mcs_image_loss_fwd(C.byref(a), C.byref(b), _LOSS_IDS.get(loss, 0), 1 if tonemapper == "log_srgb" else 0, out.data_ptr(),
+        li, ti = _loss_ids(loss, tonemapper)
+        L.check(L.lib().mcs_image_loss_fwd(C.byref(a), C.byref(b), li, ti, out.data_ptr(),
                                            L.stream_ptr()), "image_loss (forward)")
         return out
 
@@ -263,7 +275,8 @@ class _image_loss_func(torch.autograd.Function):
         d = dout.float()
         dd = L._desc(d.data_ptr(), [d.shape[0], 1, 1, 1], [d.stride(0), 0, 0, 0])
         a, b = L.nhwc(img), L.nhwc(target)
-        L.check(L.lib().mcs_image_loss_bwd(C.byref(a), C.byref(b), _LOSS_IDS.get(ctx.loss, 0), 1 if ctx.tonemapper == "log_srgb" else 0, C.byref(dd),
+        li, ti = _loss_ids(ctx.loss, ctx.tonemapper)
+        L.check(L.lib().mcs_image_loss_bwd(C.byref(a), C.byref(b), li, ti, C.byref(dd),
                                            gi.data_ptr(), gt.data_ptr(), L.stream_ptr()), "image_loss (backward)")
         return _reduce_like(gi, img), _reduce_like(gt, target), None, None
 
@@ -271,6 +284,7 @@ class _image_loss_func(torch.autograd.Function):
 def image_loss(img, target, loss='l1', tonemapper='none', use_python=False):
     """renderutils/ops.py:476-498.  HDR image loss, tonemapping + loss fused in one kernel.  loss in ['l1', 'mse', 'smape', 'relmse', 'n2n']
     (FIX: the reference's CUDA path silently computes l1 for 'n2n'), tonemapper in ['none', 'log_srgb'].  Returns a scalar."""
+    _loss_ids(loss, tonemapper)
     if use_python:
         from .loss import image_loss_fn
         out = image_loss_fn(img, target, loss, tonemapper)

@@ -141,3 +141,72 @@ def test_shard_indices_epochs():
     nxt = np.concatenate([shard_indices(12, 4, it, seed=5, rank=0, world=1).numpy() for it in range(3, 6)])
     assert sorted(nxt.tolist()) == list(range(12)) and not np.array_equal(nxt, seen)      # the next epoch is a new permutation
     assert shard_indices(3, 4, 0, seed=1, rank=0, world=2).numel() == 2           # dataset smaller than the batch wraps around
+
+
+# ---- the reference loop calls optimizer.zero_grad() (set_to_none=True) and builds a LambdaLR per optimizer ------------
+def _worker_ref_loop(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nvdiffrecmc_b200.parallel import GradBucket, hook_optimizer, shard_views
+    g = torch.Generator().manual_seed(0)
+    views = torch.rand(8, 32, generator=g)
+    # parameters owned by "modules", as in train.py:340-356; the bucket adopts them in place
+    light = torch.nn.Parameter(torch.rand(32, 3, generator=g)); tex = torch.nn.Parameter(torch.rand(32, 3, generator=g))
+    bucket = GradBucket.adopt([light, tex])
+    assert light.data_ptr() == bucket.flat.data_ptr()
+    opt = torch.optim.Adam([light, tex], lr=0.05)
+    order = rank % 2 == 0                                        # scheduler before / after the hook: both must work
+    if order:
+        sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=lambda it: 0.5 ** it)
+    hook_optimizer(opt, bucket)
+    if not order:
+        sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=lambda it: 0.5 ** it)
+    sl = shard_views(8)
+    for _ in range(3):
+        opt.zero_grad()                                          # train.py:407-411 (set_to_none=True by default)
+        _toy_loss((light, tex), views[sl]).backward()
+        opt.step()                                               # train.py:452
+        sched.step()                                             # train.py:453
+    q.put((rank, bucket.flat.detach().clone().numpy(), float(sched.get_last_lr()[0])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_reference_loop_shape_zero_grad_and_scheduler():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_ref_loop, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(2)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(0)
+    views = torch.rand(8, 32, generator=g)
+    light = torch.nn.Parameter(torch.rand(32, 3, generator=g)); tex = torch.nn.Parameter(torch.rand(32, 3, generator=g))
+    opt = torch.optim.Adam([light, tex], lr=0.05)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=lambda it: 0.5 ** it)
+    for _ in range(3):
+        opt.zero_grad()
+        _toy_loss((light, tex), views).backward()
+        opt.step(); sched.step()
+    ref = torch.cat([light.detach().reshape(-1), tex.detach().reshape(-1)]).numpy()
+    assert np.array_equal(res[0][1], res[1][1]), "ranks diverged"
+    assert np.allclose(res[0][1], ref, rtol=1e-5, atol=1e-7)
+    assert res[0][2] == res[1][2] == float(sched.get_last_lr()[0])
+
+
+def test_bucket_survives_set_to_none_without_the_hook():
+    """all_reduce_mean() must never reduce a stale bucket: foreign .grad tensors are copied in, missing ones zero their slice."""
+    from nvdiffrecmc_b200.parallel import GradBucket
+    b = GradBucket([(3,), (2,)], device="cpu")
+    opt = torch.optim.SGD(b.params, lr=0.1)
+    b.flat_grad.fill_(7.0)                                       # stale content from an earlier step
+    opt.zero_grad()                                              # drops the aliases
+    (b.params[0] * 2).sum().backward()                           # fresh .grad for params[0] only
+    assert b.params[0].grad.data_ptr() != b.flat_grad.data_ptr()
+    b.all_reduce_mean()
+    assert b.flat_grad.tolist() == [2.0, 2.0, 2.0, 0.0, 0.0]
+    assert b.params[0].grad.data_ptr() == b.flat_grad.data_ptr() and b.params[1].grad is not None

@@ -114,3 +114,16 @@ def test_docs_are_sane():
     d = open(os.path.join(root, "DESIGN.md")).read()
     for needle in ("SURVEY §8 a/b", "Oracle and parity", "Data layout in HBM", "Kernels", "Measurement", "Multi-GPU", "Out of scope", "oracle/_ref"):
         assert needle in d, needle
+
+
+def test_image_loss_rejects_unknown_names():
+    """an unknown / mistyped loss name must not silently become L1 (that is exactly the reference's 'n2n' bug,
+    renderutils/c_src/torch_bindings.cpp:727-737); same for the tonemapper."""
+    import nvdiffrecmc_b200.renderutils as ru
+    x = torch.rand(1, 4, 4, 3)
+    for kw in (dict(loss="l2"), dict(loss="N2N"), dict(tonemapper="srgb")):
+        with pytest.raises(ValueError, match="unknown"):
+            ru.image_loss(x, x, use_python=True, **kw)
+        with pytest.raises(ValueError, match="unknown"):
+            ru.image_loss(x, x, **kw)                              # native path: rejected before any device work
+    assert float(ru.image_loss(x, x, loss="n2n", tonemapper="log_srgb", use_python=True)) == 0.0
