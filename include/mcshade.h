@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define MCS_ABI_VERSION 1
+#define MCS_ABI_VERSION 2
 
 /* Strided NHWC view of fp32 (or int32) device memory.  sizes/strides are in ELEMENTS, dims are
  * (N, H, W, C); a size-1 dimension broadcasts (stride ignored), exactly like the reference's
@@ -79,13 +79,16 @@ int mcs_trace_closest(mcs_ctx *ctx, const float *ro, const float *rd, int64_t n,
  *      rec_count / rec_rays (optional, together): the full RAY RECORD -- rec_count uint32 [B,H,W] = number of rays that were
  *      evaluated for the pixel (visible, or occluded with shadow_scale < 1), rec_rays fp32 [B,H,W,5,rec_slots] =
  *      (dx, dy, dz, MIS weight, env texel | occluded << 31) in evaluation order, rec_slots >= 2*n_samples_x^2.  With it the
- *      backward pass needs neither sampling nor traversal: see mcs_env_shade_bwd_replay. */
+ *      backward pass needs neither sampling nor traversal: see mcs_env_shade_bwd_replay.
+ *      seed_offset_dev (optional, may be NULL): DEVICE pointer to one uint32 that the kernel adds to rnd_seed when it starts.  The
+ *      reference passes the seed by value from a host counter (render/render.py:19,112-116); a host value is frozen into a captured
+ *      CUDA graph, a device value is not -- the training step can be captured once and replayed with an advancing seed. */
 int mcs_env_shade_fwd(mcs_ctx *ctx,
                       const mcs_tensor *mask, const mcs_tensor *ro, const mcs_tensor *gb_pos, const mcs_tensor *gb_normal,
                       const mcs_tensor *gb_view_pos, const mcs_tensor *gb_kd, const mcs_tensor *gb_ks,
                       const mcs_tensor *light, const mcs_tensor *pdf, const mcs_tensor *rows, const mcs_tensor *cols,
                       const mcs_tensor *perms,
-                      uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
+                      uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, const uint32_t *seed_offset_dev, float shadow_scale, int32_t batch_offset,
                       float *diff, float *spec, uint32_t *hit_record, uint32_t *rec_count, float *rec_rays, int32_t rec_slots, mcs_stream stream);
 
 /* Gradient outputs: gb_pos_grad, gb_normal_grad, gb_kd_grad, gb_ks_grad contiguous [B,H,W,3]
@@ -95,7 +98,7 @@ int mcs_env_shade_bwd(mcs_ctx *ctx,
                       const mcs_tensor *gb_view_pos, const mcs_tensor *gb_kd, const mcs_tensor *gb_ks,
                       const mcs_tensor *light, const mcs_tensor *pdf, const mcs_tensor *rows, const mcs_tensor *cols,
                       const mcs_tensor *perms,
-                      uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
+                      uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, const uint32_t *seed_offset_dev, float shadow_scale, int32_t batch_offset,
                       const mcs_tensor *diff_grad, const mcs_tensor *spec_grad,
                       float *gb_pos_grad, float *gb_normal_grad, float *gb_kd_grad, float *gb_ks_grad, float *light_grad,
                       const uint32_t *hit_record /* NULL = re-trace */, mcs_stream stream);
@@ -117,7 +120,7 @@ int mcs_env_shade_records(mcs_ctx *ctx,
                           const mcs_tensor *gb_view_pos, const mcs_tensor *gb_kd, const mcs_tensor *gb_ks,
                           const mcs_tensor *light, const mcs_tensor *pdf, const mcs_tensor *rows, const mcs_tensor *cols,
                           const mcs_tensor *perms,
-                          uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
+                          uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, const uint32_t *seed_offset_dev, float shadow_scale, int32_t batch_offset,
                           float *diff, float *spec, int32_t *rec_texel, uint8_t *rec_vis, mcs_stream stream);
 
 /* ---- bilateral denoiser: replaces bilateral_denoiser_fwd / _bwd,

@@ -77,10 +77,10 @@ _SIGS = {
     "mcs_bvh_export": ([_P] * 8, C.c_int),
     "mcs_trace_visibility": ([_P, _P, _P, C.c_int64, _P, _P], C.c_int),
     "mcs_trace_closest": ([_P, _P, _P, C.c_int64, _P, _P, _P], C.c_int),
-    "mcs_env_shade_fwd": ([_P] + [_T] * 12 + [C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, _P], C.c_int),
+    "mcs_env_shade_fwd": ([_P] + [_T] * 12 + [C.c_uint32, C.c_uint32, C.c_uint32, _P, C.c_float, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, _P], C.c_int),
     "mcs_env_shade_bwd_replay": ([_T] * 6 + [C.c_uint32, C.c_uint32, C.c_float, _T, _T, _P, _P, C.c_int32] + [_P] * 6, C.c_int),
-    "mcs_env_shade_records": ([_P] + [_T] * 12 + [C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_int32, _P, _P, _P, _P, _P], C.c_int),
-    "mcs_env_shade_bwd": ([_P] + [_T] * 12 + [C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_int32, _T, _T] + [_P] * 7, C.c_int),
+    "mcs_env_shade_records": ([_P] + [_T] * 12 + [C.c_uint32, C.c_uint32, C.c_uint32, _P, C.c_float, C.c_int32, _P, _P, _P, _P, _P], C.c_int),
+    "mcs_env_shade_bwd": ([_P] + [_T] * 12 + [C.c_uint32, C.c_uint32, C.c_uint32, _P, C.c_float, C.c_int32, _T, _T] + [_P] * 7, C.c_int),
     "mcs_bilateral_fwd": ([_T, _T, _T, C.c_float, _P, _P], C.c_int),
     "mcs_bilateral_bwd": ([_T, _T, C.c_float, _T, _P, _P], C.c_int),
     "mcs_bilateral_fwd2": ([_T, _T, _T, _T, C.c_float, _P, _P, _P], C.c_int),
@@ -134,7 +134,7 @@ def lib():
         fn = getattr(l, name)          # AttributeError if the symbol is missing
         fn.argtypes = args
         fn.restype = res
-    if l.mcs_abi_version() != 1:
+    if l.mcs_abi_version() != 2:
         raise RuntimeError("libmcshade ABI version mismatch")
     _lib = l
     return l

@@ -55,6 +55,7 @@ struct EnvParams {
     int B, H, W;
     int N, S;
     uint32_t bsdf, seed;
+    const uint32_t *seed_dev;       // optional: added to `seed` at kernel start (CUDA-graph friendly seed advance)
     int batch_offset;
     float shadow_scale;
     BvhView bvh;
@@ -375,7 +376,7 @@ __device__ __forceinline__ void gen_segment(const EnvParams &p, BlockQueue &q, B
     const int qb = seg * SEG;
     const xf strata_frac = xf(1.0f) / xf((float)(unsigned)p.N);
     // RNG, kernel.cu:504-505
-    uint32_t s_seed = p.seed, s_pix = (uint32_t)(((px.iz + p.batch_offset) * p.H + px.iy) * p.W + px.ix);
+    uint32_t s_seed = p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0u), s_pix = (uint32_t)(((px.iz + p.batch_offset) * p.H + px.iy) * p.W + px.ix);
     uint32_t rng = rand_pcg(s_seed) ^ rand_pcg(s_pix);
     const uint32_t lightIdx = rand_pcg(rng) % p.n_perms;
     const uint32_t bsdfIdx = rand_pcg(rng) % p.n_perms;
@@ -948,7 +949,7 @@ static int fill_params(mcs_ctx *ctx, EnvParams &p,
                        const mcs_tensor *mask, const mcs_tensor *ro, const mcs_tensor *gb_pos, const mcs_tensor *gb_normal,
                        const mcs_tensor *gb_view_pos, const mcs_tensor *gb_kd, const mcs_tensor *gb_ks,
                        const mcs_tensor *light, const mcs_tensor *pdf, const mcs_tensor *rows, const mcs_tensor *cols,
-                       const mcs_tensor *perms, uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
+                       const mcs_tensor *perms, uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, const uint32_t *seed_offset_dev, float shadow_scale, int32_t batch_offset,
                        cudaStream_t s)
 {
     MCS_REQUIRE(ctx != nullptr, "env_shade: null context");
@@ -984,7 +985,7 @@ static int fill_params(mcs_ctx *ctx, EnvParams &p,
     MCS_REQUIRE(perms->sizes[3] == p.S && perms->sizes[1] >= 1, "env_shade: perms must be [P, n_samples_x^2]");
     p.perms = (const int32_t *)perms->ptr; p.pm_s1 = perms->strides[1]; p.pm_s3 = perms->strides[3]; p.n_perms = (uint32_t)perms->sizes[1];
     p.m_rows = cdf_iters(p.Hl); p.m_cols = cdf_iters(p.Wl);
-    p.bsdf = bsdf; p.seed = rnd_seed; p.batch_offset = batch_offset; p.shadow_scale = shadow_scale;
+    p.bsdf = bsdf; p.seed = rnd_seed; p.seed_dev = seed_offset_dev; p.batch_offset = batch_offset; p.shadow_scale = shadow_scale;
     p.bvh = BvhView{(const float4 *)ctx->nodes.p, (const float4 *)ctx->tris.p, (const float *)ctx->qgrid.p, (const uint4 *)ctx->nodesq4.p};
     if (int e = ensure_skip_table(ctx, p.N, s, &p.skip)) return e;
     // work-claim counter of the persistent grid: one slot of a small ring PER LAUNCH, so launches of the same context that are in
@@ -1023,13 +1024,13 @@ int mcs_env_shade_fwd(mcs_ctx *ctx,
                       const mcs_tensor *gb_view_pos, const mcs_tensor *gb_kd, const mcs_tensor *gb_ks,
                       const mcs_tensor *light, const mcs_tensor *pdf, const mcs_tensor *rows, const mcs_tensor *cols,
                       const mcs_tensor *perms,
-                      uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
+                      uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, const uint32_t *seed_offset_dev, float shadow_scale, int32_t batch_offset,
                       float *diff, float *spec, uint32_t *hit_record, uint32_t *rec_count, float *rec_rays, int32_t rec_slots, mcs_stream stream)
 {
     EnvParams p{};
     cudaStream_t s = (cudaStream_t)stream;
     if (int e = fill_params(ctx, p, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms, bsdf, n_samples_x, rnd_seed,
-                            shadow_scale, batch_offset, s)) return e;
+                            seed_offset_dev, shadow_scale, batch_offset, s)) return e;
     MCS_REQUIRE(diff && spec, "env_shade_fwd: null output pointer");
     p.diff = diff; p.spec = spec; p.hit_out = hit_record;
     MCS_REQUIRE((rec_count == nullptr) == (rec_rays == nullptr), "env_shade_fwd: rec_count and rec_rays go together");
@@ -1043,13 +1044,13 @@ int mcs_env_shade_records(mcs_ctx *ctx,
                           const mcs_tensor *gb_view_pos, const mcs_tensor *gb_kd, const mcs_tensor *gb_ks,
                           const mcs_tensor *light, const mcs_tensor *pdf, const mcs_tensor *rows, const mcs_tensor *cols,
                           const mcs_tensor *perms,
-                          uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
+                          uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, const uint32_t *seed_offset_dev, float shadow_scale, int32_t batch_offset,
                           float *diff, float *spec, int32_t *rec_texel, uint8_t *rec_vis, mcs_stream stream)
 {
     EnvParams p{};
     cudaStream_t s = (cudaStream_t)stream;
     if (int e = fill_params(ctx, p, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms, bsdf, n_samples_x, rnd_seed,
-                            shadow_scale, batch_offset, s)) return e;
+                            seed_offset_dev, shadow_scale, batch_offset, s)) return e;
     MCS_REQUIRE(diff && spec && rec_texel && rec_vis, "env_shade_records: null output pointer");
     p.diff = diff; p.spec = spec; p.rec_texel = rec_texel; p.rec_vis = rec_vis;
     return launch_env<2>(p, s);
@@ -1060,7 +1061,7 @@ int mcs_env_shade_bwd(mcs_ctx *ctx,
                       const mcs_tensor *gb_view_pos, const mcs_tensor *gb_kd, const mcs_tensor *gb_ks,
                       const mcs_tensor *light, const mcs_tensor *pdf, const mcs_tensor *rows, const mcs_tensor *cols,
                       const mcs_tensor *perms,
-                      uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, float shadow_scale, int32_t batch_offset,
+                      uint32_t bsdf, uint32_t n_samples_x, uint32_t rnd_seed, const uint32_t *seed_offset_dev, float shadow_scale, int32_t batch_offset,
                       const mcs_tensor *diff_grad, const mcs_tensor *spec_grad,
                       float *gb_pos_grad, float *gb_normal_grad, float *gb_kd_grad, float *gb_ks_grad, float *light_grad,
                       const uint32_t *hit_record, mcs_stream stream)
@@ -1068,7 +1069,7 @@ int mcs_env_shade_bwd(mcs_ctx *ctx,
     EnvParams p{};
     cudaStream_t s = (cudaStream_t)stream;
     if (int e = fill_params(ctx, p, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms, bsdf, n_samples_x, rnd_seed,
-                            shadow_scale, batch_offset, s)) return e;
+                            seed_offset_dev, shadow_scale, batch_offset, s)) return e;
     MCS_REQUIRE(view_ok(diff_grad) && view_ok(spec_grad), "env_shade_bwd: null / empty upstream gradient");
     MCS_REQUIRE(gb_pos_grad && gb_normal_grad && gb_kd_grad && gb_ks_grad && light_grad, "env_shade_bwd: null output pointer");
     for (int d = 0; d < 3; ++d)

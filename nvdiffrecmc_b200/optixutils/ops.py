@@ -25,9 +25,20 @@ RAY_RECORD_MAX_BYTES = 32 << 30
 RAY_RECORD_MAX_FREE_FRACTION = 0.5
 
 
+_fits_cache = {}
+
+
 def _ray_record_fits(nbytes, device):
     if nbytes > RAY_RECORD_MAX_BYTES:
         return False
+    key = (str(device), int(nbytes))
+    if torch.cuda.is_current_stream_capturing():       # no memory queries while a CUDA graph is being captured: reuse the eager decision
+        return _fits_cache.get(key, True)
+    _fits_cache[key] = _ray_record_fits_now(nbytes, device)
+    return _fits_cache[key]
+
+
+def _ray_record_fits_now(nbytes, device):
     free, _total = torch.cuda.mem_get_info(device)
     # memory cached by torch's allocator is reusable for the record even though the driver reports it as used
     free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
@@ -77,6 +88,17 @@ def optix_build_bvh(optix_ctx, verts, tris, rebuild):
     optix_ctx._version += 1
     L.check(L.lib().mcs_bvh_build(optix_ctx.cpp_wrapper, v.data_ptr(), v.shape[0], t.data_ptr(), t.shape[0], int(rebuild), L.stream_ptr()),
             "optix_build_bvh")
+
+
+def _split_seed(rnd_seed):
+    """(host uint32 seed, device pointer or None).  `rnd_seed` may be a 1-element CUDA int32 tensor: the kernel then reads the seed
+    from device memory when it RUNS (mcshade.h: seed_offset_dev), so a CUDA-graph-captured training step can advance its seed with
+    an in-graph `seed += 1` the way render.py:116 bumps the host counter."""
+    if isinstance(rnd_seed, torch.Tensor):
+        if not (rnd_seed.is_cuda and rnd_seed.dtype == torch.int32 and rnd_seed.numel() == 1):
+            raise RuntimeError("rnd_seed tensor must be a 1-element CUDA int32 tensor")
+        return 0, rnd_seed.data_ptr()
+    return int(rnd_seed) & 0xFFFFFFFF, None
 
 
 def _env_descs(mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, perms):
@@ -130,8 +152,9 @@ class _optix_env_shade_func(torch.autograd.Function):
             rec_rays = torch.empty(B, H, W, 5, slots, dtype=torch.float32, device=ro.device)
         elif mode == "bits":
             hit = torch.empty(B, H, W, (slots + 31) // 32, dtype=torch.int32, device=ro.device)
+        seed_host, seed_dev = _split_seed(_rnd_seed)
         L.check(L.lib().mcs_env_shade_fwd(optix_ctx.cpp_wrapper, *[C.byref(x) for x in d], int(BSDF), int(n_samples_x),
-                                          int(_rnd_seed) & 0xFFFFFFFF, float(shadow_scale), int(batch_offset),
+                                          seed_host, seed_dev, float(shadow_scale), int(batch_offset),
                                           diff.data_ptr(), spec.data_ptr(), hit.data_ptr() if hit is not None else None,
                                           rec_cnt.data_ptr() if rec_cnt is not None else None, rec_rays.data_ptr() if rec_rays is not None else None,
                                           slots, L.stream_ptr()),
@@ -171,8 +194,10 @@ class _optix_env_shade_func(torch.autograd.Function):
                                                      g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), g[3].data_ptr(), light_grad.data_ptr(),
                                                      L.stream_ptr()), "optix_env_shade (backward, ray-record replay)")
             return (None, None, None, g[0], g[1], None, g[2], g[3], light_grad, None, None, None, None, None, None, None, None, None)
+        # (a device seed tensor must still hold the forward pass's value here: advance it BEFORE the forward call, not after)
+        seed_host, seed_dev = _split_seed(_rnd_seed)
         L.check(L.lib().mcs_env_shade_bwd(optix_ctx.cpp_wrapper, *[C.byref(x) for x in d], int(ctx.BSDF), int(ctx.n_samples_x),
-                                          int(_rnd_seed) & 0xFFFFFFFF, float(ctx.shadow_scale), int(ctx.batch_offset),
+                                          seed_host, seed_dev, float(ctx.shadow_scale), int(ctx.batch_offset),
                                           C.byref(dg), C.byref(sg), g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), g[3].data_ptr(),
                                           light_grad.data_ptr(), hit.data_ptr() if hit is not None else None, L.stream_ptr()),
                 "optix_env_shade (backward)")
@@ -200,8 +225,9 @@ def env_shade_records(optix_ctx, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd
     spec = torch.empty(B, H, W, 3, dtype=torch.float32, device=ro.device)
     rec_t = torch.full((B, H, W, S2), -1, dtype=torch.int32, device=ro.device)
     rec_v = torch.full((B, H, W, S2), 255, dtype=torch.uint8, device=ro.device)
+    seed_host, seed_dev = _split_seed(rnd_seed)
     L.check(L.lib().mcs_env_shade_records(optix_ctx.cpp_wrapper, *[C.byref(x) for x in d], _BSDF_MODES.index(BSDF), int(n_samples_x),
-                                          int(rnd_seed) & 0xFFFFFFFF, float(shadow_scale), int(batch_offset), diff.data_ptr(), spec.data_ptr(),
+                                          seed_host, seed_dev, float(shadow_scale), int(batch_offset), diff.data_ptr(), spec.data_ptr(),
                                           rec_t.data_ptr(), rec_v.data_ptr(), L.stream_ptr()), "env_shade_records")
     return diff, spec, rec_t, rec_v
 

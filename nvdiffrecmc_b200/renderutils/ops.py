@@ -137,12 +137,26 @@ class _prepare_shading_normal_func(torch.autograd.Function):
         return tuple(_reduce_like(a, b) for a, b in zip(g, ins)) + (None, None)
 
 
+_DEFAULT_PNRM = {}
+
+
+def _default_perturbed_nrm(device):
+    """[1,1,1,3] = (0, 0, 1), created once per device (the reference builds it from a Python list on every call, ops.py:217-218 -- a
+    pageable host-to-device copy that would also break CUDA-graph capture of the step)."""
+    key = str(device)
+    if key not in _DEFAULT_PNRM:
+        t = torch.zeros(1, 1, 1, 3, dtype=torch.float32, device=device)
+        t[..., 2] = 1.0
+        _DEFAULT_PNRM[key] = t
+    return _DEFAULT_PNRM[key]
+
+
 def prepare_shading_normal(pos, view_pos, perturbed_nrm, smooth_nrm, smooth_tng, geom_nrm, two_sided_shading=True, opengl=True, use_python=False):
     """renderutils/ops.py:181-227.  Builds the tangent frame, perturbs by the normal map, flips for
     two-sided shading and bends back-facing normals towards the camera.  All tensors are
     [minibatch, height, width, 3] or broadcastable."""
     if perturbed_nrm is None:
-        perturbed_nrm = torch.tensor([0, 0, 1], dtype=torch.float32, device=pos.device, requires_grad=False)[None, None, None, ...]
+        perturbed_nrm = _default_perturbed_nrm(pos.device)
     if use_python:
         out = _tb.prepare_shading_normal(pos, view_pos, perturbed_nrm, smooth_nrm, smooth_tng, geom_nrm, two_sided_shading, opengl)
     else:

@@ -100,12 +100,29 @@ def merge(*meshes):
 def scene_mesh(kind="blob", level=4, seed=5):
     """'blob': displaced icosphere; 'blob+torus': plus a tilted ring (inter-object shadows);
     'full': plus a ground plane."""
+    if kind == "grid1m":
+        return grid1m_mesh()
+    if kind == "bob-like":        # ~11 k triangles, the size of data/bob/bob_tri.obj (10 688): blob + a finely tessellated ring
+        return merge(blob_mesh(4, seed), torus_mesh(nu=128, nv=24))
     m = [blob_mesh(level, seed)]
     if kind in ("blob+torus", "full"):
         m.append(torus_mesh())
     if kind == "full":
         m.append(plane_mesh())
     return merge(*m)
+
+
+def grid1m_mesh(n=724):
+    """BASELINE configs[4]-like ~1.08 M triangles: a displaced n x n height field (2 n^2 triangles) with an overhanging ring, so
+    that shadow rays see both a huge flat-ish occluder and inter-object shadows."""
+    g = np.linspace(-1, 1, n + 1, dtype=np.float32)
+    X, Z = np.meshgrid(g, g, indexing="ij")
+    Y = (0.25 * np.sin(7 * X) * np.cos(5 * Z) - 0.2).astype(np.float32)
+    v = np.stack([X, Y, Z], -1).reshape(-1, 3)
+    idx = np.arange((n + 1) * (n + 1)).reshape(n + 1, n + 1)
+    a, b, c, d = idx[:-1, :-1], idx[1:, :-1], idx[1:, 1:], idx[:-1, 1:]
+    f = np.concatenate([np.stack([a, c, b], -1).reshape(-1, 3), np.stack([a, d, c], -1).reshape(-1, 3)]).astype(np.int32)
+    return merge((v, f), torus_mesh(R=0.6, r=0.08, nu=256, nv=64, tilt=0.3))
 
 
 def vertex_normals(v, f):

@@ -35,9 +35,28 @@ def test_non_zero_ranks_of_the_reference_arm_stay_silent():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
-def test_physical_limiter_is_read_from_the_committed_capture():
+def test_dominant_kernel_profile_is_per_config():
+    """The physical roofline numbers (thread-instructions, DRAM bytes per launch) come from a committed ncu capture OF THE SAME CONFIG
+    (profiles/r02_dominant_kernel.json); any other configuration gets None -- never another config's constant (`traffic` was
+    the 512^2 number on the 800^2 and 1 M-triangle lines)."""
     import bench
-    p = bench.physical_limiter()
-    assert p is not None and p["limiter"] == "instruction issue" and p["source"].startswith("profiles/")
-    assert 50 < p["issue_active_pct_of_peak"] <= 100 and 1 <= p["active_lanes_per_instruction"] <= 32 and p["dram_pct_of_peak"] < 50
-    assert bench.physical_limiter("/nonexistent.json") is None          # a missing capture never breaks the bench line
+    wl = dict(bench.WORKLOAD)
+    assert bench.config_key(wl, 8) == "8x512x512_n8_blob+torus4_light256"
+    other = dict(wl, res=800)
+    assert bench.dominant_kernel_profile(other, 8) is None
+    prof = bench.dominant_kernel_profile(wl, 8)
+    if prof is not None:
+        for k in ("thread_inst_per_launch", "dram_bytes_per_launch", "rays_per_launch", "source"):
+            assert k in prof, k
+        assert prof["source"].startswith("profiles/")
+
+
+def test_coverage_balanced_deal():
+    import bench
+    import numpy as np
+    cover = np.random.default_rng(0).integers(60000, 110000, size=64)
+    order = bench.deal_views(cover, 8, 8)
+    assert sorted(order) == list(range(64))
+    per_rank = [int(sum(cover[g] for g in order[r * 8:(r + 1) * 8])) for r in range(8)]
+    assert (max(per_rank) - min(per_rank)) / np.mean(per_rank) < 0.01          # rays per rank within 1 %
+    assert bench.deal_views(cover[:8], 1, 8) == list(np.argsort(-cover[:8], kind="stable"))

@@ -18,7 +18,7 @@ def test_library_is_built_in_tree_and_loads():
     assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build()"
     assert os.path.commonpath([ROOT, os.path.abspath(_lib.LIB_PATH)]) == ROOT
     l = _lib.lib()
-    assert l.mcs_abi_version() == 1
+    assert l.mcs_abi_version() == 2
 
 
 def test_every_declared_symbol_is_exported_and_bound():
@@ -35,7 +35,7 @@ def test_header_is_plain_c():
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "t.c")
-        open(c, "w").write('#include "mcshade.h"\nint main(void){ mcs_tensor t; (void)t; return MCS_ABI_VERSION == 1 ? 0 : 1; }\n')
+        open(c, "w").write('#include "mcshade.h"\nint main(void){ mcs_tensor t; (void)t; return MCS_ABI_VERSION == 2 ? 0 : 1; }\n')
         subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", c, "-o", os.path.join(d, "t.o")], check=True)
 
 
