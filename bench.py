@@ -301,33 +301,53 @@ class GpuWorkload:
         return self.step()
 
 
-def time_env_kernels(w, reps=20, warm=5):
-    """CUDA-event time of the fused env_shade forward and backward launches alone (stream = torch current stream): median of `reps`
-    after `warm` untimed launches (median of >= 20 after 5 warm-ups); each launch draws a new seed, i.e. new rays."""
+def time_env_kernels(w, reps=20, warm=5, full=False, shadow_scale=1.0):
+    """CUDA-event time of the fused env_shade forward launch (with the ray record, as the training step issues it) and of the
+    replay backward launch ALONE: the C-ABI entry points are called directly on preallocated buffers, events on the launching
+    stream (torch's current stream) immediately around each launch, so no allocator or autograd time is inside the brackets.
+    Median of `reps` after `warm` untimed launches (median of >= 20 after 5 warm-ups); a new seed (new rays) per launch."""
+    import ctypes as C
     import torch
     import nvdiffrecmc_b200.renderutils as ru
-    ou, gb, wl = w.ou, w.gb, w.wl
+    from nvdiffrecmc_b200 import _lib as L
+    from nvdiffrecmc_b200.optixutils import ops
+    gb, wl = w.gb, w.wl
     N = wl["n_samples_x"]
     with torch.no_grad():
-        nrm0 = ru.prepare_shading_normal(gb["pos"], gb["view"], None, gb["smooth_nrm"], gb["tangent"], gb["geom_nrm"])
-        ro = gb["pos"] + nrm0 * 0.001
-        kd0 = w.kd_tex[gb["texel"]].detach(); ks0 = w.ks_tex[gb["texel"]].detach()
+        nrm = ru.prepare_shading_normal(gb["pos"], gb["view"], None, gb["smooth_nrm"], gb["tangent"], gb["geom_nrm"])
+        ro = gb["pos"] + nrm * 0.001
+        kd = w.kd_tex.detach()[gb["texel"]].contiguous(); ks = w.ks_tex.detach()[gb["texel"]].contiguous()
+        light = w.lgt.base.detach().contiguous()
+    B, H, W_ = ro.shape[:3]
+    dev = ro.device
+    slots = 2 * N * N
+    d = ops._env_descs(gb["mask"], ro, gb["pos"], nrm, gb["view"], kd, ks, light, w.lgt._pdf, w.lgt.rows[:, 0], w.lgt.cols, w.perms)
+    diff = torch.empty(B, H, W_, 3, device=dev); spec = torch.empty_like(diff)
+    rec_cnt = torch.empty(B, H, W_, dtype=torch.int32, device=dev)
+    rec_rays = torch.empty(B, H, W_, 5, slots, device=dev)
+    g = [torch.empty(B, H, W_, 3, device=dev) for _ in range(4)]
+    lg = torch.empty(light.shape[0], light.shape[1], 3, device=dev)
+    gd = torch.ones_like(diff); gs = torch.ones_like(spec)
+    dsc = [L.nhwc(gb["pos"]), L.nhwc(nrm), L.nhwc(gb["view"]), L.nhwc(kd), L.nhwc(ks), L.view_hwc(light)]
+    dg, sg = L.nhwc(gd), L.nhwc(gs)
+    lib, sp = L.lib(), L.stream_ptr()
     fw, bw = [], []
     for r in range(reps + warm):
-        nrm = nrm0.clone().requires_grad_(True); kd = kd0.clone().requires_grad_(True); ks = ks0.clone().requires_grad_(True)
-        light = w.lgt.base.detach().clone().requires_grad_(True)
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e[0].record()
-        d, s = ou.optix_env_shade(w.ctx, gb["mask"], ro, gb["pos"], nrm, gb["view"], kd, ks, light, w.lgt._pdf, w.lgt.rows[:, 0], w.lgt.cols,
-                                  n_samples_x=N, rnd_seed=1000 + r, perms=w.perms, batch_offset=w.offset)
+        L.check(lib.mcs_env_shade_fwd(w.ctx.cpp_wrapper, *[C.byref(x) for x in d], 0, N, 1000 + r, None, float(shadow_scale), int(w.offset), diff.data_ptr(), spec.data_ptr(),
+                                      None, rec_cnt.data_ptr(), rec_rays.data_ptr(), slots, sp), "optix_env_shade (forward)")
         e[1].record()
-        gd, gs = torch.ones_like(d), torch.ones_like(s)
         e[2].record()
-        torch.autograd.backward([d, s], [gd, gs])
+        L.check(lib.mcs_env_shade_bwd_replay(*[C.byref(x) for x in dsc], 0, N, float(shadow_scale), C.byref(dg), C.byref(sg), rec_cnt.data_ptr(), rec_rays.data_ptr(), slots,
+                                             g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), g[3].data_ptr(), lg.data_ptr(), sp),
+                "optix_env_shade (backward, ray-record replay)")
         e[3].record()
         torch.cuda.synchronize()
         if r >= warm:
             fw.append(e[0].elapsed_time(e[1])); bw.append(e[2].elapsed_time(e[3]))
+    if full:
+        return fw, bw
     return float(np.median(fw)), float(np.median(bw))
 
 
@@ -755,6 +775,7 @@ def main():
     names = ["ref0", "ref1", "rfwd0", "rfwd1", "fwd0", "fwd1", "bwd0", "bwd1"]
     timers = [{n: torch.cuda.Event(enable_timing=True) for n in names} for _ in range(3)]
     es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w.step()                      # graph capture emptied the allocator cache: let the eager path re-acquire its blocks first
     barrier()
     es0.record()
     for t in timers:

@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256) k_emit_nodesq(int T, const int32_t *__res
         const float m = frexpf(fmaxf(ext, 1e-30f) * (1.0f / 65532.0f), &e);  // value = m * 2^e, m in [0.5, 1)
         const int k = (m == 0.5f) ? e - 1 : e;
         inv_cell[a] = ldexpf(1.0f, -k);
-        if (i == 0) { qgrid[a] = org[a]; qgrid[3 + a] = ldexpf(1.0f, k); }
+        if (i == 0) { qgrid[a] = org[a]; qgrid[3 + a] = ldexpf(1.0f, k); qgrid[6 + a] = inv_cell[a]; }
     }
     const bool tiny = T <= MCS_LEAF_MAX;
     if (tiny ? i != 0 : i >= T - 1) return;
@@ -284,6 +284,12 @@ __global__ void __launch_bounds__(256) k_emit_nodesq(int T, const int32_t *__res
             gn[ng] = g1; gcode[ng] = child_code(g1, T, range); ++ng;
         }
     }
+    // child words: the payload (internal: node index; leaf run: (first triangle << 3) | (count - 1)) in the low 28 bits; the top
+    // nibble of slot 0 flags which of the four slots are leaf runs, so the walker classifies all four with one shift and two ANDs.
+    // Unused slots are flagged as leaves with an inverted box (never entered).
+    uint32_t leaf_bits = 0u;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) leaf_bits |= (gcode[c] < 0 ? 1u : 0u) << c;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         uint32_t ql[3] = {65535u, 65535u, 65535u}, qh[3] = {0u, 0u, 0u};
@@ -296,7 +302,8 @@ __global__ void __launch_bounds__(256) k_emit_nodesq(int T, const int32_t *__res
                 qh[a] = (uint32_t)fminf(fmaxf(fh, 0.0f), 65535.0f);
             }
         }
-        nodesq4[4 * (size_t)i + c] = make_uint4(ql[0] | (qh[0] << 16), ql[1] | (qh[1] << 16), ql[2] | (qh[2] << 16), (uint32_t)gcode[c]);
+        const uint32_t payload = (uint32_t)(gcode[c] < 0 ? ~gcode[c] : gcode[c]) & 0x0FFFFFFFu;
+        nodesq4[4 * (size_t)i + c] = make_uint4(ql[0] | (qh[0] << 16), ql[1] | (qh[1] << 16), ql[2] | (qh[2] << 16), payload | (c == 0 ? leaf_bits << 28 : 0u));
     }
 }
 
@@ -356,6 +363,7 @@ int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris
     MCS_REQUIRE(verts && tris, "mcs_bvh_build: null geometry pointer");
     // ops.py:131-132: "Got empty training triangle mesh (unrecoverable discontinuity)"
     MCS_REQUIRE(T > 0 && V > 0, "Got empty training triangle mesh (unrecoverable discontinuity)");
+    MCS_REQUIRE(T <= (1 << 25), "mcs_bvh_build: at most 2^25 triangles (28-bit child words of the quantised nodes), got %d", T);
     MCS_REQUIRE(rebuild != 0 || c->T == T, "mcs_bvh_build: refit (rebuild=0) needs an existing structure with the same triangle count (have %d, got %d)", c->T, T);
     const size_t nT = (size_t)T, nN = 2 * nT - 1;
     if (int e = mcs_buf_reserve(c->bounds, 12 * sizeof(uint32_t), s)) return e;
@@ -375,7 +383,7 @@ int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris
     if (int e = mcs_buf_reserve(c->nodes, nT * 4 * sizeof(float4), s)) return e;
     if (int e = mcs_buf_reserve(c->tris, nT * 3 * sizeof(float4), s)) return e;
     if (int e = mcs_buf_reserve(c->nodesq4, nT * 4 * sizeof(uint4), s)) return e;
-    if (int e = mcs_buf_reserve(c->qgrid, 8 * sizeof(float), s)) return e;
+    if (int e = mcs_buf_reserve(c->qgrid, 16 * sizeof(float), s)) return e;
 
     uint32_t *bounds = (uint32_t *)c->bounds.p;
     float *tlo = (float *)c->tlo.p, *thi = (float *)c->thi.p;

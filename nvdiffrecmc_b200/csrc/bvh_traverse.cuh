@@ -29,7 +29,7 @@ __device__ __forceinline__ F8 ldg256(const void *p)
 struct BvhView {
     const float4 *nodes;
     const float4 *tris;
-    const float *qgrid;      // origin xyz, cell xyz of the quantisation grid
+    const float *qgrid;      // origin xyz, cell xyz, 1 / cell xyz of the quantisation grid
     const uint4 *nodesq4;    // 64-byte 4-wide quantised nodes (bvh.cu:k_emit_nodesq, wide part); may be null
 };
 

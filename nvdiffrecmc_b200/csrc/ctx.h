@@ -31,7 +31,7 @@ struct mcs_ctx {
     DevBuf nodes;                // [max(T-1,1)] x 4 float4 (two child boxes + child codes)
     DevBuf tris;                 // [T] x 3 float4 in SORTED order: (v0, orig id), (e1, -), (e2, -)
     DevBuf nodesq4;              // [max(T-1,1)] x 4 uint4: 4-wide quantised view (the <= 4 grandchildren of binary node i), 16-bit boxes on a scene-wide grid
-    DevBuf qgrid;                // 6 floats: grid origin xyz, cell size xyz
+    DevBuf qgrid;                // 9 floats: grid origin xyz, cell size xyz, 1 / cell size xyz
     // ---- env_shade support ----
     DevBuf lcg_skip[MCS_SKIP_TABLES];   // [5*N*N+3] x uint2 (mul, add) LCG jump-ahead tables, one per cached n_samples_x
     int skip_N[MCS_SKIP_TABLES] = {0, 0, 0, 0};

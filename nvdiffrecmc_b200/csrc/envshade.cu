@@ -281,11 +281,14 @@ __device__ __forceinline__ float warp_sum(float v)
 #ifndef MCS_CTA_WARPS
 #define MCS_CTA_WARPS 8
 #endif
+#ifndef MCS_QSTACK
+#define MCS_QSTACK 100
+#endif
 #ifndef MCS_LEAF_BATCH
 #define MCS_LEAF_BATCH 32
 #endif
 #ifndef MCS_REFILL_BELOW
-#define MCS_REFILL_BELOW 16
+#define MCS_REFILL_BELOW 24               // idle lanes are refilled when fewer than this many are walking (picking up a ray is cheap: rayq_fetch)
 #endif
 constexpr int NW = MCS_CTA_WARPS;
 constexpr int SEG = 128;                 // queue entries per warp segment (= one pixel at N = 8)
@@ -303,6 +306,7 @@ struct BlockQueue {
     uint32_t hitw[NW][SEG / 32];         // per segment: occluded bits of the current queue fill
     uint2 pl[NW][PCAP];                  // per warp: deferred leaf tests, x = queue entry, y = leaf code
     float ro[NW][3];                     // per segment: ray origin / view vector / pixel id / live-ray count / fetch cursor
+    float rog[NW][3];                    // per segment: quantisation-grid origin - ray origin (rounded once, rayq_fetch)
     float wo[NW][3];
     int pixid[NW];
     int seg_cnt[NW];
@@ -367,6 +371,58 @@ __device__ __forceinline__ void make_frame(const PixelIn &q, PixelFrame &f)
     f.NdotV = xdot(f.N, f.wo);
 }
 
+// Per-ray constants of the quantised node test (bvh.cu:k_emit_nodesq): plane t = (origin + q * cell - o) / d = q' * A + B with
+// q' = 2^23 + q (the float whose low mantissa bits are the 16-bit coordinate), A = cell / d (exact: cell is a power of two),
+// B = (origin - o) / d - 2^23 * A.  |error| < 0.51 cell (rounding of B), covered by the two-cell inflation of the stored boxes.
+// The byte-permute that builds q' also picks the entry / exit plane from the (lo | hi << 16) word: its selector depends on the
+// sign of d only, so the slab test needs no min/max per axis.  Zero direction components are nudged to +-1e-20 (keeps 2^23 * A
+// finite for any sane scene; same conservative argument as ray_pre's 1e-30).
+struct RayQ {
+    float ax, ay, az, bx, by, bz;
+    uint32_t nx, ny, nz, fx, fy, fz; // PRMT selectors of the entry / exit planes (0x7410 = low half, 0x7432 = high half)
+};
+// None of these constants is part of the parity contract: culling only has to be CONSERVATIVE (the boolean result comes from the
+// exact triangle predicate), and the stored boxes carry a margin of two cells per side against a decode error of ~0.52 cell.  So
+// 1/d is one MUFU.RCP (relative error 2^-23: < 0.02 cell over the whole grid) instead of an IEEE division -- picking up a ray
+// costs half the instructions, which is what allows refilling idle lanes early (MCS_REFILL_BELOW).
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ RayQ rayq_fetch(const float *__restrict__ g, const float *rog, float dx, float dy, float dz)
+{
+    RayQ r;
+    const float ix = rcp_approx(fabsf(dx) < 1e-20f ? copysignf(1e-20f, dx) : dx);
+    const float iy = rcp_approx(fabsf(dy) < 1e-20f ? copysignf(1e-20f, dy) : dy);
+    const float iz = rcp_approx(fabsf(dz) < 1e-20f ? copysignf(1e-20f, dz) : dz);
+    r.ax = __ldg(g + 3) * ix; r.ay = __ldg(g + 4) * iy; r.az = __ldg(g + 5) * iz;
+    r.bx = fmaf(-8388608.0f, r.ax, rog[0] * ix);
+    r.by = fmaf(-8388608.0f, r.ay, rog[1] * iy);
+    r.bz = fmaf(-8388608.0f, r.az, rog[2] * iz);
+    r.nx = dx < 0.0f ? 0x7432u : 0x7410u; r.ny = dy < 0.0f ? 0x7432u : 0x7410u; r.nz = dz < 0.0f ? 0x7432u : 0x7410u;
+    r.fx = dx < 0.0f ? 0x7410u : 0x7432u; r.fy = dy < 0.0f ? 0x7410u : 0x7432u; r.fz = dz < 0.0f ? 0x7410u : 0x7432u;
+    return r;
+}
+// prmt.b32 directly: __byte_perm() masks its selector with 0x7777 first (one LOP3 per use); these selectors never set the
+// sign-replication bits.
+__device__ __forceinline__ float qplane(uint32_t w, uint32_t sel)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x4B000000u), "r"(sel));
+    return __uint_as_float(r);
+}
+// Slab test against one quantised child box.  Conservative without any relaxation of the comparison: every decoded plane is within
+// 0.52 cell (in t * |d| units) of the true plane of the STORED box, and the stored box is the padded node box rounded outward and
+// inflated by two more cells per side (bvh.cu:k_emit_nodesq), so each computed entry is below and each computed exit above the
+// true ones of the node box: a ray that meets the node box at some t >= 0 always passes.  The upper end of the ray interval
+// (t < 1e16) is enforced by the triangle test; not clamping the exit here only admits more boxes.
+__device__ __forceinline__ bool qslab(const uint4 c, const RayQ &r)
+{
+    const float a0 = fmaf(qplane(c.x, r.nx), r.ax, r.bx), a1 = fmaf(qplane(c.x, r.fx), r.ax, r.bx);
+    const float b0 = fmaf(qplane(c.y, r.ny), r.ay, r.by), b1 = fmaf(qplane(c.y, r.fy), r.ay, r.by);
+    const float c0 = fmaf(qplane(c.z, r.nz), r.az, r.bz), c1 = fmaf(qplane(c.z, r.fz), r.az, r.bz);
+    const float tn = fmaxf(fmaxf(a0, b0), fmaxf(c0, 0.0f));
+    const float tf = fminf(fminf(a1, b1), c1);
+    return tn <= tf;
+}
+
 // ---- phase G: generate the items [w0, w1) of one pixel, push the rays that can contribute into segment `seg` ----------
 template <int MODE>
 __device__ __forceinline__ void gen_segment(const EnvParams &p, BlockQueue &q, BlockQueueRec *qr, const PixelIn &px, const PixelFrame &f,
@@ -383,13 +439,18 @@ __device__ __forceinline__ void gen_segment(const EnvParams &p, BlockQueue &q, B
     const uint32_t rng2 = rng;
     const f3 nrm = px.nrm;
 
+    // Two stages (MODE 0 / 1).  Stage A draws the direction of every sample (all lanes busy) and ballot-compacts the LIVE ones --
+    // n.wi > 0 -- into the queue; stage B runs the rest of the sample set-up (lat-long texel of the direction: atan2 + acos + two
+    // double divisions, light pdf, and for light samples the BSDF pdf) on the compacted list only, i.e. not for the ~27 % of the
+    // samples that are dropped anyway.  Same operations on the same values in the same order per sample: results are bit-identical
+    // to the single-stage path, which MODE 2 keeps because it records the texel of every sample, dropped or not.
     for (int base = w0; base < w1; base += 32) {
         const int w = base + lane;
         const bool valid = w < w1;
         const bool is_bsdf = w >= S;
         const int i = is_bsdf ? w - S : w;
         xf3 dir = X3(xf(0.0f), xf(0.0f), xf(1.0f));
-        float pdf_sum = 1.0f;
+        float pdf_sum = 1.0f, pdf_b = 0.0f;
         int tx = 0, ty = 0;
         if (valid) {
             const uint2 sk = __ldg(p.skip + 5 * i + (is_bsdf ? 2 : 0));
@@ -398,21 +459,20 @@ __device__ __forceinline__ void gen_segment(const EnvParams &p, BlockQueue &q, B
             const uint32_t perm = (uint32_t)__ldg(p.perms + (size_t)row * p.pm_s1 + (size_t)i * p.pm_s3);
             const xf sx = (xf((float)(perm % (uint32_t)p.N)) + uniform_pcg(st)) * strata_frac;
             const xf sy = (xf((float)(perm / (uint32_t)p.N)) + uniform_pcg(st)) * strata_frac;
-            float cy;
             if (!is_bsdf) {
                 // lightSample, kernel.cu:184-193
                 uint32_t cyi, cxi;
                 xf ry = sample_cdf(p.rows, p.r_s, p.Hl, p.m_rows, sy, cyi);
                 xf rx = sample_cdf(p.cols + (size_t)cyi * p.c_s1, p.c_s2, p.Wl, p.m_cols, sx, cxi);
                 dir = tc_to_dir((xf((float)cxi) + rx) / xf((float)p.Wl), (xf((float)cyi) + ry) / xf((float)p.Hl));
-                dir_to_texel(p, dir, tx, ty, cy);
-                pdf_sum = light_pdf_value(p, tx, ty, cy) + bsdf_pdf_value(f, dir);
             } else {
                 const xf sz = uniform_pcg(st);
-                float pdf_b;
                 dir = bsdf_sample(f, sx, sy, sz, pdf_b);
+            }
+            if (MODE == 2) {
+                float cy;
                 dir_to_texel(p, dir, tx, ty, cy);
-                pdf_sum = light_pdf_value(p, tx, ty, cy) + pdf_b;
+                pdf_sum = light_pdf_value(p, tx, ty, cy) + (is_bsdf ? pdf_b : bsdf_pdf_value(f, dir));
             }
         }
         const f3 wi = toF3(dir);
@@ -428,48 +488,32 @@ __device__ __forceinline__ void gen_segment(const EnvParams &p, BlockQueue &q, B
         if (live) {
             const int e = qb + qn + __popc(m & ((1u << lane) - 1u));
             q.dx[e] = wi.x; q.dy[e] = wi.y; q.dz[e] = wi.z;
-            q.mis[e] = 1.0f / fmaxf(pdf_sum, 0.0001f);          // MIS balance heuristic, kernel.cu:409
-            q.tex[e] = (uint32_t)((ty << 16) | tx);
+            if (MODE == 2) {
+                q.mis[e] = 1.0f / fmaxf(pdf_sum, 0.0001f);      // MIS balance heuristic, kernel.cu:409
+                q.tex[e] = (uint32_t)((ty << 16) | tx);
+                qr->slot[e] = (uint32_t)(2 * i + (is_bsdf ? 1 : 0));
+            } else {
+                q.mis[e] = pdf_b;                               // stage B turns these two into the MIS weight and the texel
+                q.tex[e] = is_bsdf ? 1u : 0u;
+            }
             q.qitem[e] = (uint8_t)(w - w0);
-            if (MODE == 2) qr->slot[e] = (uint32_t)(2 * i + (is_bsdf ? 1 : 0));
         }
         qn += __popc(m);
     }
-}
-
-// Per-ray constants of the quantised node test (bvh.cu:k_emit_nodesq): plane t = (origin + q * cell - o) / d = q' * A + B with
-// q' = 2^23 + q (the float whose low mantissa bits are the 16-bit coordinate), A = cell / d (exact: cell is a power of two),
-// B = (origin - o) / d - 2^23 * A.  |error| < 0.51 cell (rounding of B), covered by the two-cell inflation of the stored boxes.
-// The byte-permute that builds q' also picks the entry / exit plane from the (lo | hi << 16) word: its selector depends on the
-// sign of d only, so the slab test needs no min/max per axis.  Zero direction components are nudged to +-1e-20 (keeps 2^23 * A
-// finite for any sane scene; same conservative argument as ray_pre's 1e-30).
-struct RayQ {
-    float ax, ay, az, bx, by, bz;
-    uint32_t nx, ny, nz;             // PRMT selectors of the entry plane (0x7410 = low half, 0x7432 = high half); exit = ^ 0x0022
-};
-__device__ __forceinline__ RayQ rayq_pre(const float *__restrict__ g, f3 o, f3 d)
-{
-    const float dx = fabsf(d.x) < 1e-20f ? copysignf(1e-20f, d.x) : d.x;
-    const float dy = fabsf(d.y) < 1e-20f ? copysignf(1e-20f, d.y) : d.y;
-    const float dz = fabsf(d.z) < 1e-20f ? copysignf(1e-20f, d.z) : d.z;
-    const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
-    RayQ r;
-    r.ax = __ldg(g + 3) * ix; r.ay = __ldg(g + 4) * iy; r.az = __ldg(g + 5) * iz;
-    r.bx = __fmaf_rn(-8388608.0f, r.ax, __fmul_rn(__fsub_rn(__ldg(g), o.x), ix));
-    r.by = __fmaf_rn(-8388608.0f, r.ay, __fmul_rn(__fsub_rn(__ldg(g + 1), o.y), iy));
-    r.bz = __fmaf_rn(-8388608.0f, r.az, __fmul_rn(__fsub_rn(__ldg(g + 2), o.z), iz));
-    r.nx = dx < 0.0f ? 0x7432u : 0x7410u; r.ny = dy < 0.0f ? 0x7432u : 0x7410u; r.nz = dz < 0.0f ? 0x7432u : 0x7410u;
-    return r;
-}
-__device__ __forceinline__ float qplane(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)); }
-__device__ __forceinline__ bool qslab(const uint4 c, const RayQ &r, float &tn)
-{
-    const float a0 = fmaf(qplane(c.x, r.nx), r.ax, r.bx), a1 = fmaf(qplane(c.x, r.nx ^ 0x22u), r.ax, r.bx);
-    const float b0 = fmaf(qplane(c.y, r.ny), r.ay, r.by), b1 = fmaf(qplane(c.y, r.ny ^ 0x22u), r.ay, r.by);
-    const float c0 = fmaf(qplane(c.z, r.nz), r.az, r.bz), c1 = fmaf(qplane(c.z, r.nz ^ 0x22u), r.az, r.bz);
-    tn = fmaxf(fmaxf(a0, b0), fmaxf(c0, 0.0f));
-    const float tf = fminf(fminf(a1, b1), fminf(c1, MCS_TMAX));
-    return tn <= tf * 1.0000004f;
+    if (MODE != 2) {
+        __syncwarp();
+        for (int e0 = 0; e0 < qn; e0 += 32) {
+            const int e = qb + e0 + lane;
+            if (e0 + lane < qn) {
+                const xf3 dir = X3(xf(q.dx[e]), xf(q.dy[e]), xf(q.dz[e]));
+                int tx, ty; float cy;
+                dir_to_texel(p, dir, tx, ty, cy);
+                const float pdf_sum = light_pdf_value(p, tx, ty, cy) + (q.tex[e] ? q.mis[e] : bsdf_pdf_value(f, dir));
+                q.mis[e] = 1.0f / fmaxf(pdf_sum, 0.0001f);      // MIS balance heuristic, kernel.cu:409
+                q.tex[e] = (uint32_t)((ty << 16) | tx);
+            }
+        }
+    }
 }
 
 // ---- phase T: any-hit traversal of all queued rays of the CTA: work stealing + dynamic fetch + deferred leaf tests ----
@@ -499,8 +543,8 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
     int pend = 0;
     int my = -1;
     int node = 0, sp = 0;
-    int stack[96];                               // up to 3 pushes per visit (1.5 per binary level; MCS_STACK = 64 covers the binary walk)
-    RayQ r; r.ax = r.ay = r.az = 1.0f; r.bx = r.by = r.bz = 0.0f; r.nx = r.ny = r.nz = 0x7410u;
+    int stack[MCS_QSTACK];                       // up to 3 pushes per visit (1.5 per binary level of the LBVH walk) + one scratch slot
+    RayQ r; r.ax = r.ay = r.az = 1.0f; r.bx = r.by = r.bz = 0.0f; r.nx = r.ny = r.nz = 0x7410u; r.fx = r.fy = r.fz = 0x7432u;
     const BvhView b = p.bvh;
     uint2 *pl = q.pl[warp];
     int seg = warp, exhausted = 0;           // segment being drained, number of segments found empty so far
@@ -513,7 +557,7 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
             const uint2 ent = pl[base + lane];
             const int e = (int)ent.x;
             if (!(q.tex[e] >> 31)) {
-                const int code = ~(int)ent.y;
+                const int code = (int)ent.y;             // leaf run: (first triangle << 3) | (count - 1)
                 const int start = code >> 3, cnt = (code & 7) + 1;
                 const int ps = e / SEG;
                 const f3 o = F3(q.ro[ps][0], q.ro[ps][1], q.ro[ps][2]);
@@ -547,7 +591,7 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
             if (my < 0 && rank < take) {
                 const int idx = seg * SEG + base + rank;
                 my = idx;
-                r = rayq_pre(b.qgrid, F3(q.ro[seg][0], q.ro[seg][1], q.ro[seg][2]), F3(q.dx[idx], q.dy[idx], q.dz[idx]));
+                r = rayq_fetch(b.qgrid, q.rog[seg], q.dx[idx], q.dy[idx], q.dz[idx]);
                 node = 0; sp = 0;
             }
             if (take < need) { seg = seg + 1 == NW ? 0 : seg + 1; ++exhausted; }
@@ -567,22 +611,20 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
             if (my >= 0) {
                 const uint4 *n = b.nodesq4 + 4 * (size_t)node;
                 const uint4 k0 = __ldg(n), k1 = __ldg(n + 1), k2 = __ldg(n + 2), k3 = __ldg(n + 3);
-                float tn;
-                const bool h0 = qslab(k0, r, tn), h1 = qslab(k1, r, tn), h2 = qslab(k2, r, tn), h3 = qslab(k3, r, tn);
-                c0 = (int)k0.w; c1 = (int)k1.w; c2 = (int)k2.w; c3 = (int)k3.w;
-                const bool p0 = h0 && c0 >= 0, p1 = h1 && c1 >= 0, p2 = h2 && c2 >= 0, p3 = h3 && c3 >= 0;
-                lmask = (h0 && c0 < 0 ? 1u : 0u) | (h1 && c1 < 0 ? 2u : 0u) | (h2 && c2 < 0 ? 4u : 0u) | (h3 && c3 < 0 ? 8u : 0u);
-                // internal children hit: push them all (predicated stores; any-hit: the order does not change the result), continue
-                // with the last one straight from its register (its stack slot is released again); nothing hit -> pop
-                if (p0) stack[sp] = c0;
-                sp += p0 ? 1 : 0;
-                if (p1) stack[sp] = c1;
-                sp += p1 ? 1 : 0;
-                if (p2) stack[sp] = c2;
-                sp += p2 ? 1 : 0;
-                if (p3) stack[sp] = c3;
-                sp += p3 ? 1 : 0;
-                if (p0 || p1 || p2 || p3) { node = p3 ? c3 : (p2 ? c2 : (p1 ? c1 : c0)); --sp; }
+                const bool h0 = qslab(k0, r), h1 = qslab(k1, r), h2 = qslab(k2, r), h3 = qslab(k3, r);
+                const unsigned hm = (h0 ? 1u : 0u) | (h1 ? 2u : 0u) | (h2 ? 4u : 0u) | (h3 ? 8u : 0u);
+                const unsigned lb = k0.w >> 28;                       // which of the four children are leaf runs (bvh.cu:k_emit_nodesq)
+                c0 = (int)(k0.w & 0x0FFFFFFFu); c1 = (int)k1.w; c2 = (int)k2.w; c3 = (int)k3.w;
+                lmask = hm & lb;
+                const unsigned im = hm & ~lb;
+                // internal children hit: push them all with UNCONDITIONAL stores and a conditional stack-pointer bump (a slot above
+                // sp is scratch), continue with the last one straight from its register (its slot is released again); nothing hit ->
+                // pop.  any-hit: the visiting order does not change the result.
+                stack[sp] = c0; sp += (int)(im & 1u);
+                stack[sp] = c1; sp += (int)((im >> 1) & 1u);
+                stack[sp] = c2; sp += (int)((im >> 2) & 1u);
+                stack[sp] = c3; sp += (int)(im >> 3);
+                if (im) { node = (im & 8u) ? c3 : ((im & 4u) ? c2 : ((im & 2u) ? c1 : c0)); --sp; }
                 else if (sp) node = stack[--sp];
                 else my = -1;                               // walk finished; verdict comes from the occluded bit
             }
@@ -692,6 +734,8 @@ __global__ void __launch_bounds__(NW * 32, 32 / NW) env_shade_kernel(const EnvPa
                 PixelFrame f;
                 make_frame(px, f);
                 if (lane < 3) {
+                    const float ro_l = lane == 0 ? px.ro.x : (lane == 1 ? px.ro.y : px.ro.z);
+                    q.rog[warp][lane] = __fsub_rn(__ldg(p.bvh.qgrid + lane), ro_l);
                     q.ro[warp][lane] = lane == 0 ? px.ro.x : (lane == 1 ? px.ro.y : px.ro.z);
                     q.wo[warp][lane] = lane == 0 ? f.wo.x.v : (lane == 1 ? f.wo.y.v : f.wo.z.v);
                 }

@@ -11,9 +11,9 @@ if len(sys.argv) > 2: wl["res"] = int(sys.argv[2])
 if len(sys.argv) > 3: wl["n_samples_x"] = int(sys.argv[3])
 dev = torch.device("cuda:0")
 w = bench.GpuWorkload(wl, 0, 1, dev)
-if "KB_SHADOW" in os.environ:            # e.g. KB_SHADOW=0: skip the trace phase entirely (sampling + shading cost alone)
-    _orig = w.ou.optix_env_shade
-    w.ou.optix_env_shade = lambda *a, **k: _orig(*a, shadow_scale=float(os.environ["KB_SHADOW"]), **k)
-f, b = bench.time_env_kernels(w, reps=5, warm=2)
-print(json.dumps({"lib": os.environ.get("MCS_LIB", "default"), "views": wl["views_per_gpu"], "fwd_ms": round(f, 3), "bwd_ms": round(b, 3),
-                  "fwd_mrays": round(w.rays_per_pass / f / 1e3, 1), "bwd_mrays": round(w.rays_per_pass / b / 1e3, 1)}))
+import numpy as np
+fw, bw = bench.time_env_kernels(w, reps=int(os.environ.get("KB_REPS", 12)), warm=3, full=True, shadow_scale=float(os.environ.get("KB_SHADOW", 1.0)))   # KB_SHADOW=0: no trace phase
+f, b = float(np.median(fw)), float(np.median(bw))
+print(json.dumps({"lib": os.path.basename(os.environ.get("MCS_LIB", "default")), "views": wl["views_per_gpu"], "config_key": bench.config_key(wl, wl["views_per_gpu"]),
+                  "rays_per_launch": w.rays_per_pass, "fwd_ms": round(f, 3), "fwd_min_max": [round(min(fw), 2), round(max(fw), 2)],
+                  "bwd_ms": round(b, 3), "fwd_mrays": round(w.rays_per_pass / f / 1e3, 1), "bwd_mrays": round(w.rays_per_pass / b / 1e3, 1)}))

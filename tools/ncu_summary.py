@@ -47,8 +47,35 @@ def launches(path, out, desc):
     print("wrote", out)
 
 
+def dominant(rep, kbench_log, out, source):
+    """profiles/r02_dominant_kernel.json: per-config physical numbers of env_shade_kernel<0> that bench.py's roofline reads."""
+    import os
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    d = dict(zip(rows[0], rows[2])); u = dict(zip(rows[0], rows[1]))
+    kb = json.loads([l for l in open(kbench_log) if l.startswith("{")][-1])
+    num = lambda k: float(d[k].replace(",", ""))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    dram = num("dram__bytes_read.sum") * scale[u["dram__bytes_read.sum"]] + num("dram__bytes_write.sum") * scale[u["dram__bytes_write.sum"]]
+    winst, lanes = num("smsp__inst_executed.sum"), num("smsp__thread_inst_executed_per_inst_executed.ratio")
+    entry = {"kernel": d["Kernel Name"], "rays_per_launch": kb["rays_per_launch"], "warp_inst_per_launch": int(winst), "lanes_per_inst": lanes,
+             "thread_inst_per_launch": int(winst * lanes), "dram_bytes_per_launch": int(dram), "kernel_ms_under_ncu": num("gpu__time_duration.sum"),
+             "issue_active_pct": round(num("smsp__issue_active.avg.pct_of_peak_sustained_active"), 1),
+             "alu_pipe_pct": round(num("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"), 1),
+             "fma_pipe_pct": round(num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"), 1),
+             "xu_pipe_pct": round(num("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"), 1),
+             "l1_hit_pct": round(num("l1tex__t_sector_hit_rate.pct"), 1), "source": source}
+    allc = json.load(open(out)) if os.path.exists(out) else {"what": "ncu --set full --clock-control none capture of env_shade_kernel<0> per bench configuration "
+                                                                      "(tools/ncu_env.sh); bench.py's roofline reads the entry of ITS configuration or reports null", "configs": {}}
+    allc["configs"][kb["config_key"]] = entry
+    json.dump(allc, open(out, "w"), indent=1)
+    print("wrote", out, kb["config_key"])
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "--launches":
+    if sys.argv[1] == "--dominant":
+        dominant(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5])
+    elif sys.argv[1] == "--launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4])
     else:
         full(sys.argv[1], sys.argv[2], sys.argv[3])
