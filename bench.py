@@ -583,6 +583,15 @@ def quiet_stdout():
     os.dup2(2, 1)
 
 
+def hard_exit():
+    """Leave without tearing down NCCL communicators / captured graphs: with the all-reduce captured inside CUDA graphs,
+    `destroy_process_group()` was observed to block for minutes after the result line had been printed (rank 0 works alone on the
+    parity / CPU legs long after the other ranks are done).  All results are flushed; the OS reclaims the rest."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def emit(obj):
     sys.stdout.flush()
     if _STDOUT_FD is not None:
@@ -864,9 +873,7 @@ def main():
         barrier()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        hard_exit()
 
     # ---- rank 0: parity of this launch configuration, roofline of the dominant kernel, CPU baseline -----------------------------
     parity = None
@@ -971,8 +978,7 @@ def main():
         "cpu_baseline": cpu,
     }
     emit(out)
-    if world > 1:
-        dist.destroy_process_group()
+    hard_exit()
 
 
 if __name__ == "__main__":

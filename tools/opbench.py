@@ -50,6 +50,26 @@ for shape in [(1, 256, 256), (16, 512, 512), (1, 2048, 2048)]:          # test_b
                            "algorithmic_bytes_per_px": [fwd_bytes, bwd_bytes]})
         print(out["ops"][-1], flush=True)
 
+# tail of shade(): denoiser normalisation + demodulated recombination (render.py:119-131), 8 x 512 x 512
+B, H, W = 8, 512, 512
+a4 = (torch.rand(B, H, W, 4, generator=g) + 0.5).to(dev).requires_grad_(True); b4 = (torch.rand(B, H, W, 4, generator=g) + 0.5).to(dev).requires_grad_(True)
+kdc = torch.rand(B, H, W, 3, generator=g).to(dev).requires_grad_(True); ksc = torch.rand(B, H, W, 3, generator=g).to(dev).requires_grad_(True)
+from nvdiffrecmc_b200.optixutils.ops import shade_combine
+with torch.no_grad():
+    ms_f = timed(lambda: shade_combine(a4.detach(), b4.detach(), kdc.detach(), ksc.detach()))
+yc = shade_combine(a4, b4, kdc, ksc)
+gyc = torch.rand_like(yc)
+ms_b = timed(lambda: torch.autograd.grad(yc, [a4, b4, kdc, ksc], gyc, retain_graph=True))
+npx = B * H * W
+out["shade_combine"] = {"shape": [B, H, W], "fwd_ms": round(ms_f, 4), "fwd_gbs_at_68B_per_px": round(npx * 68 / ms_f / 1e6, 1), "fwd_frac_of_hbm_peak": round(npx * 68 / ms_f / 1e6 / peak, 3),
+                        "bwd_ms": round(ms_b, 4), "bwd_gbs_at_124B_per_px": round(npx * 124 / ms_b / 1e6, 1), "bwd_frac_of_hbm_peak": round(npx * 124 / ms_b / 1e6 / peak, 3)}
+print(out["shade_combine"], flush=True)
+
+if os.environ.get("OPB_ONLY") == "ew":
+    if len(sys.argv) > 1:
+        json.dump(out, open(sys.argv[1], "w"), indent=1)
+    sys.exit(0)
+
 # bilateral denoiser, sigma = 2 (23 x 23 taps), 8 x 512 x 512
 B, H, W = 8, 512, 512
 col = torch.rand(B, H, W, 3, generator=g).to(dev).requires_grad_(True)
