@@ -65,7 +65,11 @@ __global__ void __launch_bounds__(256) k_tri_bounds(const float *__restrict__ ve
             thi[3 * (size_t)t + a] = hi[a];
         }
     }
-    // warp-aggregated min/max, one atomic per warp per value
+    // warp shuffle reduction -> shared-memory atomics -> ONE set of 12 global atomics per CTA.  (One set per WARP, as in round 1, is
+    // 400 k atomics on 12 addresses at 1 M triangles: 260 us, the largest item of the 715 us rebuild -- profiles/r02_bvh_build.json.)
+    __shared__ uint32_t sb[12];
+    if (threadIdx.x < 12) sb[threadIdx.x] = ((threadIdx.x / 3) & 1) ? 0u : 0xFFFFFFFFu;
+    __syncthreads();
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         float cmn = valid ? c[a] : INFINITY, cmx = valid ? c[a] : -INFINITY, smn = lo[a], smx = hi[a];
@@ -77,11 +81,16 @@ __global__ void __launch_bounds__(256) k_tri_bounds(const float *__restrict__ ve
             smx = fmaxf(smx, __shfl_xor_sync(0xFFFFFFFFu, smx, o));
         }
         if ((threadIdx.x & 31) == 0 && cmn <= cmx) {
-            atomicMin(bounds + a, f2ord(cmn));
-            atomicMax(bounds + 3 + a, f2ord(cmx));
-            atomicMin(bounds + 6 + a, f2ord(smn));
-            atomicMax(bounds + 9 + a, f2ord(smx));
+            atomicMin(sb + a, f2ord(cmn));
+            atomicMax(sb + 3 + a, f2ord(cmx));
+            atomicMin(sb + 6 + a, f2ord(smn));
+            atomicMax(sb + 9 + a, f2ord(smx));
         }
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        if ((threadIdx.x / 3) & 1) atomicMax(bounds + threadIdx.x, sb[threadIdx.x]);
+        else atomicMin(bounds + threadIdx.x, sb[threadIdx.x]);
     }
 }
 
@@ -206,7 +215,7 @@ __global__ void __launch_bounds__(256) k_leaves_refit(const float *__restrict__ 
 // Traversal nodes: node i holds the boxes of its two children.  A child whose subtree covers at most
 // MCS_LEAF_MAX triangles is emitted as a leaf run (the triangles of an LBVH subtree are consecutive in
 // Morton order); the internal nodes below it are simply never referenced.
-__device__ __forceinline__ int child_code(int c, int T, const int2 *__restrict__ range)
+__device__ __forceinline__ int child_code(int c, int T, const int2 *range)
 {
     if (c >= T - 1) return ~(((c - (T - 1)) << 3) | 0);
     const int2 r = range[c];
@@ -214,11 +223,9 @@ __device__ __forceinline__ int child_code(int c, int T, const int2 *__restrict__
     return cnt <= MCS_LEAF_MAX ? ~((r.x << 3) | (cnt - 1)) : c;
 }
 
-__global__ void __launch_bounds__(256) k_emit_nodes(int T, const int32_t *__restrict__ left, const int32_t *__restrict__ right,
-                                                    const int2 *__restrict__ range, const float *__restrict__ lo, const float *__restrict__ hi,
-                                                    float4 *__restrict__ nodes)
+__device__ __forceinline__ void emit_node(int i, int T, const int32_t *left, const int32_t *right, const int2 *range, const float *lo, const float *hi,
+                                          float4 *nodes)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (T <= MCS_LEAF_MAX) {
         if (i == 0) {   // tiny mesh: the root is one leaf run; child 1 is an empty box (node 0 of lo/hi is the root box, or the only leaf)
             nodes[0] = make_float4(lo[0], hi[0], lo[1], hi[1]);
@@ -247,11 +254,9 @@ __global__ void __launch_bounds__(256) k_emit_nodes(int T, const int32_t *__rest
 // the entry / exit plane by the sign of the ray direction.  Boxes are rounded outward and inflated by two more cells per side,
 // which covers the quantisation rounding and the < 0.51-cell error of the biased decode: culling stays conservative, the
 // visibility result is unchanged (tests/test_gpu_envshade.py records tests, incl. a 330 k-triangle mesh).
-__global__ void __launch_bounds__(256) k_emit_nodesq(int T, const int32_t *__restrict__ left, const int32_t *__restrict__ right,
-                                                     const int2 *__restrict__ range, const float *__restrict__ lo, const float *__restrict__ hi,
-                                                     uint4 *__restrict__ nodesq4, float *__restrict__ qgrid)
+__device__ __forceinline__ void emit_nodeq(const int i, int T, const int32_t *left, const int32_t *right, const int2 *range, const float *lo, const float *hi,
+                                           uint4 *nodesq4, float *qgrid)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float org[3], inv_cell[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -305,6 +310,15 @@ __global__ void __launch_bounds__(256) k_emit_nodesq(int T, const int32_t *__res
         const uint32_t payload = (uint32_t)(gcode[c] < 0 ? ~gcode[c] : gcode[c]) & 0x0FFFFFFFu;
         nodesq4[4 * (size_t)i + c] = make_uint4(ql[0] | (qh[0] << 16), ql[1] | (qh[1] << 16), ql[2] | (qh[2] << 16), payload | (c == 0 ? leaf_bits << 28 : 0u));
     }
+}
+
+// one launch for both node views (large-mesh path)
+__global__ void __launch_bounds__(256) k_emit_both(int T, const int32_t *left, const int32_t *right, const int2 *range, const float *lo, const float *hi,
+                                                   float4 *nodes, uint4 *nodesq4, float *qgrid)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    emit_node(i, T, left, right, range, lo, hi, nodes);
+    emit_nodeq(i, T, left, right, range, lo, hi, nodesq4, qgrid);
 }
 
 typedef BvhView VisView;
@@ -391,6 +405,10 @@ int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris
     k_tri_bounds<<<nblk(T, 256), 256, 0, s>>>(verts, tris, T, tlo, thi, bounds);
     MCS_LAUNCH_CHECK();
     if (rebuild) {
+        // Measured and dropped for the small meshes (7-11 k triangles, where the radix sort is six latency-bound launches = 52 of the
+        // rebuild's 136 us of kernel time): a hand-written single-CTA shared-memory bitonic sort of 64-bit (key, id) composites -- correct
+        // (bit-identical structure) but 60-140 us on one SM; and the whole rebuild as ONE single-CTA launch -- 522 us (seven dependent
+        // gather / refit chains per thread instead of seven CTAs' worth of parallel ones).  profiles/r02_bvh_build.json.
         k_morton<<<nblk(T, 256), 256, 0, s>>>(tlo, thi, T, bounds, (uint32_t *)c->keys.p, (int32_t *)c->vals.p);
         MCS_LAUNCH_CHECK();
         size_t tmp_bytes = 0;
@@ -410,11 +428,9 @@ int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris
                                                 (const int32_t *)c->right.p, (const int32_t *)c->parent.p, (float *)c->lo.p, (float *)c->hi.p,
                                                 (int *)c->flags.p, (float4 *)c->tris.p);
     MCS_LAUNCH_CHECK();
-    k_emit_nodes<<<nblk(T > 1 ? T - 1 : 1, 256), 256, 0, s>>>(T, (const int32_t *)c->left.p, (const int32_t *)c->right.p, (const int2 *)c->range.p,
-                                                              (const float *)c->lo.p, (const float *)c->hi.p, (float4 *)c->nodes.p);
-    MCS_LAUNCH_CHECK();
-    k_emit_nodesq<<<nblk(T > 1 ? T - 1 : 1, 256), 256, 0, s>>>(T, (const int32_t *)c->left.p, (const int32_t *)c->right.p, (const int2 *)c->range.p,
-                                                               (const float *)c->lo.p, (const float *)c->hi.p, (uint4 *)c->nodesq4.p, (float *)c->qgrid.p);
+    k_emit_both<<<nblk(T > 1 ? T - 1 : 1, 256), 256, 0, s>>>(T, (const int32_t *)c->left.p, (const int32_t *)c->right.p, (const int2 *)c->range.p,
+                                                              (const float *)c->lo.p, (const float *)c->hi.p, (float4 *)c->nodes.p, (uint4 *)c->nodesq4.p,
+                                                              (float *)c->qgrid.p);
     MCS_LAUNCH_CHECK();
     c->T = T; c->V = V;
     return 0;
