@@ -852,6 +852,8 @@ def main():
             s_ms /= args.steps
             strong = {"global_batch": gbs, "views_per_gpu": gbs // world, "ms_per_step": round(s_ms, 3), "train_iters_per_s": round(1e3 / s_ms, 3),
                       "cuda_graph": s_status,
+                      "rays_per_pass_min_max_over_ranks": [int(-max_over_ranks(-float(ws.rays_per_pass), world, dev, torch, dist)),
+                                                           int(max_over_ranks(float(ws.rays_per_pass), world, dev, torch, dist))],
                       "mrays_per_s": round(sum_over_ranks(ws.rays_per_pass, world, dev, torch, dist) * PASSES / (s_ms * 1e-3) / 1e6, 2)}
         else:
             ws = None
