@@ -293,7 +293,10 @@ __device__ __forceinline__ float warp_sum(float v)
 constexpr int NW = MCS_CTA_WARPS;
 constexpr int SEG = 128;                 // queue entries per warp segment (= one pixel at N = 8)
 constexpr int QTOT = NW * SEG;
-constexpr int PCAP = 160;                // pending (ray, leaf) pairs per warp: < 32 carried over + at most 128 appended per node step
+#ifndef MCS_PCAP
+#define MCS_PCAP 160             // 64 (flush inside the deferral loop, 6 KB less smem, 132 KB carve-out => 124 KB of L1) measured +5.6 %: profiles/r02_envshade_ab.json
+#endif
+constexpr int PCAP = MCS_PCAP;           // pending (ray, leaf) pairs per warp: < 32 carried over + at most 128 appended per node step
 constexpr int PIXRING = 256;
 static_assert(QTOT <= 65536, "queue entry index is stored in 16 bits");
 static_assert(SEG <= 256 && SEG % 32 == 0, "sample slot within a fill is stored in 8 bits");
@@ -637,6 +640,7 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
                     lmask ^= low;
                 }
                 pend += __popc(mL);
+                if (PCAP < 160 && pend >= LEAF_BATCH) leaf_batch(32);     // (only for the small-list variant)
             }
             nact = __popc(__ballot_sync(0xFFFFFFFFu, my >= 0));
         } while (pend < LEAF_BATCH && nact >= thresh);
@@ -1048,6 +1052,14 @@ static int launch_env(const EnvParams &p, cudaStream_t s)
     MCS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const size_t smem = sizeof(BlockQueue) + (MODE == 2 ? sizeof(BlockQueueRec) : 0);
     MCS_CUDA(cudaFuncSetAttribute(env_shade_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // Shared memory and L1 share 256 KB per SM and the carve-out comes in steps (..., 100, 132, 164, 196, 228 KB): ask for exactly what
+    // 32 / NW resident CTAs need, so that everything else stays L1 for the BVH nodes, triangles and probe tables (36 KB per CTA => the
+    // 164 KB step, 92 KB of L1).
+    {
+        const size_t need = (size_t)(32 / NW) * (smem + 1024);
+        int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+        MCS_CUDA(cudaFuncSetAttribute(env_shade_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
+    }
     MCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, env_shade_kernel<MODE>, NW * 32, smem));
     if (per_sm < 1) per_sm = 1;
     const int64_t npix = (int64_t)p.B * p.H * p.W;
