@@ -9,6 +9,8 @@ wl = dict(bench.WORKLOAD)
 if len(sys.argv) > 1: wl["views_per_gpu"] = int(sys.argv[1])
 if len(sys.argv) > 2: wl["res"] = int(sys.argv[2])
 if len(sys.argv) > 3: wl["n_samples_x"] = int(sys.argv[3])
+if os.environ.get("KB_MESH"): wl["mesh"] = os.environ["KB_MESH"]
+if os.environ.get("KB_LEVEL"): wl["mesh_level"] = int(os.environ["KB_LEVEL"])
 dev = torch.device("cuda:0")
 w = bench.GpuWorkload(wl, 0, 1, dev)
 import numpy as np

@@ -1,9 +1,9 @@
 #!/bin/bash
-# usage (on the GPU box): tools/ncu_env.sh <variant-name|default> <out-prefix> [views] -- one `ncu --set full` capture of env_shade_kernel<0> on the bench workload
+# usage (on the GPU box): [KB_MESH=.. KB_LEVEL=..] tools/ncu_env.sh <variant-name|default> <out-prefix> [views] [res] [n_samples_x] -- one `ncu --set full` capture of env_shade_kernel<0> on the bench workload
 set -e
-v=$1; out=$2; views=${3:-8}
+v=$1; out=$2; views=${3:-8}; res=${4:-512}; n=${5:-8}
 if [ "$v" != "default" ]; then export MCS_LIB=nvdiffrecmc_b200/lib/variants/$v.so; fi
-KB_REPS=1 ncu --set full --clock-control none --import-source on -k regex:env_shade_kernel -s 3 -c 1 -f -o gpurun_out/$out python tools/kbench.py $views > gpurun_out/$out.log 2>&1
+KB_REPS=1 ncu --set full --clock-control none --import-source on -k regex:env_shade_kernel -s 3 -c 1 -f -o gpurun_out/$out python tools/kbench.py $views $res $n > gpurun_out/$out.log 2>&1
 ncu -i gpurun_out/$out.ncu-rep --page raw --csv 2>/dev/null | python -c "
 import csv,sys
 rows=list(csv.reader(sys.stdin)); h=rows[0]
