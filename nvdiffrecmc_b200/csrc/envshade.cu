@@ -281,6 +281,12 @@ __device__ __forceinline__ float warp_sum(float v)
 #ifndef MCS_CTA_WARPS
 #define MCS_CTA_WARPS 8
 #endif
+#ifndef MCS_SPLIT_WALKS
+#define MCS_SPLIT_WALKS 1
+#endif
+#ifndef MCS_SPLIT_BELOW
+#define MCS_SPLIT_BELOW 20
+#endif
 #ifndef MCS_QSTACK
 #define MCS_QSTACK 100
 #endif
@@ -545,7 +551,7 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
     int pend = 0;
     int my = -1;
-    int node = 0, sp = 0;
+    int node = 0, sp = 0, sb = 0;                // stack = entries [sb, sp): the owner pops at the top, idle lanes are handed the bottom
     int stack[MCS_QSTACK];                       // up to 3 pushes per visit (1.5 per binary level of the LBVH walk) + one scratch slot
     RayQ r; r.ax = r.ay = r.az = 1.0f; r.bx = r.by = r.bz = 0.0f; r.nx = r.ny = r.nz = 0x7410u; r.fx = r.fy = r.fz = 0x7432u;
     const BvhView b = p.bvh;
@@ -595,18 +601,43 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
                 const int idx = seg * SEG + base + rank;
                 my = idx;
                 r = rayq_fetch(b.qgrid, q.rog[seg], q.dx[idx], q.dy[idx], q.dz[idx]);
-                node = 0; sp = 0;
+                node = 0; sp = 0; sb = 0;
             }
             if (take < need) { seg = seg + 1 == NW ? 0 : seg + 1; ++exhausted; }
             idle = __ballot_sync(0xFFFFFFFFu, my < 0);
         }
+#if MCS_SPLIT_WALKS
+        // ---- drain: nothing left to fetch.  The last rays of a batch are the long walks, and a warp used to finish them at a handful of
+        // lanes (22.9 / 32 lanes on average over the whole kernel, profiles/r02_envshade_ab.json).  An any-hit walk is a set of
+        // independent subtrees, so idle lanes take the BOTTOM stack entry (the largest pending subtree) of busy lanes and walk it for
+        // the same ray: the k-th idle lane pairs with the k-th lane that has something to give.  The verdict is the ray's occluded
+        // bit, set by whichever lane finds a hit -- the result cannot depend on who walks what.
+        if (exhausted >= NW && idle) {
+            const unsigned donors = __ballot_sync(0xFFFFFFFFu, my >= 0 && sp > sb);
+            if (donors) {
+                const int npair = min(__popc(idle), __popc(donors));
+                const bool give = my >= 0 && sp > sb && __popc(donors & lt) < npair;
+                const int bottom = give ? stack[sb] : 0;
+                if (give) ++sb;
+                const bool take = my < 0 && __popc(idle & lt) < npair;
+                const int src = take ? (int)__fns(donors, 0u, __popc(idle & lt) + 1) : lane;
+                const int got = __shfl_sync(0xFFFFFFFFu, bottom, src), ray = __shfl_sync(0xFFFFFFFFu, my, src);
+                if (take) {
+                    my = ray; node = got; sp = 0; sb = 0;
+                    const int ps = ray / SEG;
+                    r = rayq_fetch(b.qgrid, q.rog[ps], q.dx[ray], q.dy[ray], q.dz[ray]);
+                }
+            }
+        }
+#endif
         int nact = __popc(__ballot_sync(0xFFFFFFFFu, my >= 0));
         if (nact == 0) {
             if (pend == 0) break;
             leaf_batch(pend < 32 ? pend : 32);        // final flush (nothing left to fetch, no walker left)
             continue;
         }
-        const int thresh = exhausted < NW ? REFILL_BELOW : 1;
+        // while draining, come back here after every node step that leaves lanes idle, so that they can be handed subtrees
+        const int thresh = exhausted < NW ? REFILL_BELOW : (MCS_SPLIT_WALKS ? MCS_SPLIT_BELOW : 1);
         do {
             const int cur = my;
             unsigned lmask = 0u;
@@ -628,7 +659,7 @@ __device__ __forceinline__ void trace_queue(const EnvParams &p, BlockQueue &q, c
                 stack[sp] = c2; sp += (int)((im >> 2) & 1u);
                 stack[sp] = c3; sp += (int)(im >> 3);
                 if (im) { node = (im & 8u) ? c3 : ((im & 4u) ? c2 : ((im & 2u) ? c1 : c0)); --sp; }
-                else if (sp) node = stack[--sp];
+                else if (sp > sb) node = stack[--sp];
                 else my = -1;                               // walk finished; verdict comes from the occluded bit
             }
             // defer the leaf tests: one (ray, leaf run) pair per leaf child hit, one ballot round per pair of the busiest lane

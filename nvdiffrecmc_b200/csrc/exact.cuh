@@ -89,12 +89,16 @@ __device__ MCS_DET_INLINE void det_sincos(xf a, xf &s, xf &c)
     default: s = -cp; c = sp;  break;
     }
 }
+// Range reduction of atan: t > tan(3pi/8): pi/2 + atan(-1/t); t > tan(pi/8): pi/4 + atan((t-1)/(t+1)); else atan(t).  The three ranges
+// share ONE division with selected operands -- (-1)/t == -(1/t) and t/1 == t exactly -- so a warp whose lanes fall into different
+// ranges (nearly always) executes one IEEE division instead of two divergent ones; the values are bit-identical to the branchy form.
 __device__ __forceinline__ xf det_atan_pos(xf t)
 {
-    xf y0;
-    if (t.v > 2.414213562373095f)       { y0 = xf(1.57079632679489661923f); t = -(xf(1.0f) / t); }
-    else if (t.v > 0.4142135623730950f) { y0 = xf(0.78539816339744830962f); t = (t - xf(1.0f)) / (t + xf(1.0f)); }
-    else                                { y0 = xf(0.0f); }
+    const bool hi = t.v > 2.414213562373095f, mid = !hi && t.v > 0.4142135623730950f;
+    const xf y0 = xf(hi ? 1.57079632679489661923f : (mid ? 0.78539816339744830962f : 0.0f));
+    const xf num = hi ? xf(-1.0f) : (mid ? t - xf(1.0f) : t);
+    const xf den = hi ? t : (mid ? t + xf(1.0f) : xf(1.0f));
+    t = num / den;
     xf z = t * t;
     xf y = (((xf(8.05374449538e-2f) * z - xf(1.38776856032e-1f)) * z + xf(1.99777106478e-1f)) * z - xf(3.33329491539e-1f)) * z * t + t;
     return y0 + y;
@@ -111,9 +115,16 @@ __device__ __forceinline__ xf det_asin_kernel(xf a)
     xf z = a * a;
     return ((((xf(4.2163199048e-2f) * z + xf(2.4181311049e-2f)) * z + xf(4.5470025998e-2f)) * z + xf(7.4953002686e-2f)) * z + xf(1.6666752422e-1f)) * z * a + a;
 }
+// acos through ONE evaluation of the asin kernel: |x| > 0.5 uses 2 asin(sqrt((1 - |x|) / 2)) (1 - |x| is 1 + x for negative x, exactly),
+// otherwise pi/2 - asin(x).  Same operations on the same values as the three-branch form (oracle/detmath.h), without executing the
+// polynomial up to three times per warp.
 __device__ MCS_DET_INLINE xf det_acos(xf x)
 {
-    if (x.v < -0.5f) return xf(3.14159265358979323846f) - xf(2.0f) * det_asin_kernel(xsqrt(xf(0.5f) * (xf(1.0f) + x)));
-    if (x.v > 0.5f) return xf(2.0f) * det_asin_kernel(xsqrt(xf(0.5f) * (xf(1.0f) - x)));
-    return xf(1.57079632679489661923f) - det_asin_kernel(x);
+    const bool big = x.v < -0.5f || x.v > 0.5f;
+    const xf om = x.v < 0.0f ? xf(1.0f) + x : xf(1.0f) - x;
+    const xf a = big ? xsqrt(xf(0.5f) * om) : x;
+    const xf k = det_asin_kernel(a);
+    if (x.v < -0.5f) return xf(3.14159265358979323846f) - xf(2.0f) * k;
+    if (x.v > 0.5f) return xf(2.0f) * k;
+    return xf(1.57079632679489661923f) - k;
 }
