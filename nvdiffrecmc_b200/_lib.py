@@ -140,11 +140,10 @@ def lib():
     return l
 
 
-# Count of OUR kernels launched through the C ABI (bench.py's gpu_launches claim).  optix_build_bvh launches seven hand-written
-# kernels (bounds init, triangle bounds, Morton codes, Karras topology, leaves + refit, fp32 node emission, quantised node emission)
-# around one CUB radix sort.
+# Count of OUR kernels launched through the C ABI (bench.py's gpu_launches claim).  optix_build_bvh launches eleven hand-written
+# kernels: bounds init, triangle bounds, Morton codes, radix sort (histogram + 4 passes), Karras topology, leaves + refit, node emission.
 LAUNCHES = collections.Counter()
-_KERNELS_PER_CALL = {"optix_build_bvh": 7, "bvh_export": 0, "update_pdf": 2, "rasterize": 2}
+_KERNELS_PER_CALL = {"optix_build_bvh": 11, "bvh_export": 0, "update_pdf": 2, "rasterize": 2}
 
 
 def check(status, what):

@@ -11,14 +11,13 @@
 //   1. tri_bounds  : per-triangle AABB + reduction of centroid / scene bounds (order-preserving
 //                    uint encoding + atomicMin/Max, warp-aggregated)
 //   2. morton      : 30-bit Morton code of the AABB centre normalised to the centroid bounds
-//   3. sort        : stable LSD radix sort of (code, triangle id)  [cub::DeviceRadixSort, 30 bits]
+//   3. sort        : stable LSD radix sort of (code, triangle id), hand-written onesweep (k_rs_hist_all + 4 x k_rs_pass), 30 bits
 //   4. karras      : Karras-2012 topology, one thread per internal node
 //   5. leaves+refit: padded leaf boxes, sorted triangle records (v0,e1,e2 as 3 x float4), bottom-up
 //                    box union with arrival counters (second thread to arrive continues)
 //   6. emit        : 64-byte fp32 binary traversal nodes holding both children's boxes (stand-alone visibility / closest-hit queries)
 //   7. emit_nodesq : 16-bit quantised child records on a scene-wide power-of-two grid, as a 4-wide (4 x 16 B: the grandchildren
 //                    of binary node i) view of the same tree -- what the fused kernel's shadow rays walk
-#include <cub/cub.cuh>
 #include "bvh_traverse.cuh"
 #include "ctx.h"
 
@@ -122,6 +121,147 @@ __global__ void __launch_bounds__(256) k_morton(const float *__restrict__ tlo, c
     vals[t] = t;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Hand-written stable LSD radix sort of (Morton key, triangle id) pairs: 30-bit keys, four passes of 8 / 8 / 8 / 6 bits, one launch
+// per pass ("onesweep": Adinets & Merrill 2022).  A launch of the upfront histogram kernel counts all four digits of every key once
+// (global digit totals do not depend on the order); each pass kernel then
+//   * takes tiles of RS_TILE = 4096 consecutive keys in TICKET order (an atomic counter: a tile's predecessors are always resident or
+//     done, so the look-back below cannot deadlock);
+//   * counts the tile's digits per warp (warp w owns 512 consecutive keys, walked in 16 rounds of 32 in index order);
+//   * publishes the tile's digit counts and obtains its global offsets by DECOUPLED LOOK-BACK over the predecessors' flags (thread d
+//     handles digit d: walk back until an inclusive prefix is found, adding aggregates on the way);
+//   * scatters: rank within a round by __match_any_sync (lanes with the same digit, ordered by lane), rounds and warps in order, so
+//     equal keys keep their input order -- the order of the oracle's qsort by (key, id) because ids start in increasing order.
+// Replaces cub::DeviceRadixSort::SortPairs (round 1) with the same launch count; no library code is left in the rebuild.
+// ---------------------------------------------------------------------------------------------
+#define RS_THREADS 256
+#define RS_ITEMS 16
+#define RS_TILE (RS_THREADS * RS_ITEMS)
+#define RS_FLAG_AGG 0x40000000u
+#define RS_FLAG_PREFIX 0x80000000u
+#define RS_VALUE_MASK 0x3FFFFFFFu
+
+__host__ __device__ __forceinline__ int rs_shift(int pass) { return 8 * pass; }
+__host__ __device__ __forceinline__ uint32_t rs_mask(int pass) { return pass == 3 ? 0x3Fu : 0xFFu; }
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist_all(const uint32_t *__restrict__ keys, int T, uint32_t *__restrict__ G)
+{
+    __shared__ uint32_t h[4][256];
+    for (int i = threadIdx.x; i < 1024; i += RS_THREADS) (&h[0][0])[i] = 0u;
+    __syncthreads();
+    const int base = blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const int i = base + k * RS_THREADS + threadIdx.x;
+        if (i < T) {
+            const uint32_t key = keys[i];
+            atomicAdd(&h[0][key & 0xFFu], 1u); atomicAdd(&h[1][(key >> 8) & 0xFFu], 1u);
+            atomicAdd(&h[2][(key >> 16) & 0xFFu], 1u); atomicAdd(&h[3][(key >> 24) & 0x3Fu], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 1024; i += RS_THREADS) {
+        const uint32_t v = (&h[0][0])[i];
+        if (v) atomicAdd(G + i, v);
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_pass(const uint32_t *__restrict__ keys_in, const int32_t *__restrict__ vals_in, uint32_t *__restrict__ keys_out,
+                                                        int32_t *__restrict__ vals_out, int T, int pass, const uint32_t *__restrict__ G, unsigned int *ticket,
+                                                        volatile uint32_t *flags)
+{
+    __shared__ uint32_t wc[RS_THREADS / 32][256];     // per-warp digit counts -> per-warp running output offsets
+    __shared__ uint32_t dbase[256];                   // exclusive scan of the global digit totals
+    __shared__ unsigned int s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int shift = rs_shift(pass);
+    const uint32_t mask = rs_mask(pass);
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < (RS_THREADS / 32) * 256; i += RS_THREADS) (&wc[0][0])[i] = 0u;
+    {   // exclusive scan of G[pass][0..255] (one value per thread: warp scan + warp totals)
+        const uint32_t g = __ldg(G + pass * 256 + tid);
+        uint32_t x = g;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+        __shared__ uint32_t wtot[RS_THREADS / 32];
+        if (lane == 31) wtot[warp] = x;
+        __syncthreads();
+        uint32_t off = 0;
+        for (int w = 0; w < warp; ++w) off += wtot[w];
+        dbase[tid] = off + x - g;
+    }
+    __syncthreads();
+    const int tile = (int)s_tile;
+    const int wbase = tile * RS_TILE + warp * (RS_TILE / (RS_THREADS / 32));
+    // ---- digits of this warp's 512 keys, in index order; per-warp counts ----
+    uint32_t key[RS_ITEMS]; int32_t val[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const int i = wbase + r * 32 + lane;
+        const bool ok = i < T;
+        key[r] = ok ? keys_in[i] : 0xFFFFFFFFu;
+        val[r] = ok ? vals_in[i] : 0;
+        if (ok) atomicAdd(&wc[warp][(key[r] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    // ---- digit d = tid: tile count, look-back, per-warp exclusive offsets ----
+    {
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) cnt += wc[w][tid];
+        volatile uint32_t *my_flag = flags + (size_t)tile * 256 + tid;
+        *my_flag = cnt | RS_FLAG_AGG;
+        uint32_t run = 0;
+        for (int j = tile - 1; j >= 0; --j) {
+            uint32_t f;
+            do { f = flags[(size_t)j * 256 + tid]; } while (f == 0u);
+            run += f & RS_VALUE_MASK;
+            if (f & RS_FLAG_PREFIX) break;
+        }
+        __threadfence();
+        *my_flag = ((run + cnt) & RS_VALUE_MASK) | RS_FLAG_PREFIX;
+        uint32_t off = dbase[tid] + run;
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) { const uint32_t c = wc[w][tid]; wc[w][tid] = off; off += c; }
+    }
+    __syncthreads();
+    // ---- stable scatter: rounds in order, lanes in order within a digit ----
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const bool ok = (wbase + r * 32 + lane) < T;
+        const uint32_t d = ok ? ((key[r] >> shift) & mask) : 0x1FFu;
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        uint32_t pos = 0;
+        if (ok) pos = wc[warp][d];
+        __syncwarp();
+        if (ok && rank == 0) wc[warp][d] = pos + (uint32_t)__popc(peers);
+        __syncwarp();
+        if (ok) { keys_out[pos + rank] = key[r]; vals_out[pos + rank] = val[r]; }
+    }
+}
+
+static int rs_sort_pairs(uint32_t *keys_a, int32_t *vals_a, uint32_t *keys_b, int32_t *vals_b, int T, DevBuf &work, cudaStream_t s)
+{
+    // input in (keys_a, vals_a); four passes a -> b -> a -> b -> a: the sorted pairs end in (keys_a, vals_a)
+    const int ntiles = (T + RS_TILE - 1) / RS_TILE;
+    const size_t words = 4 * 256 + 4 + (size_t)4 * ntiles * 256;
+    if (int e = mcs_buf_reserve(work, words * sizeof(uint32_t), s)) return e;
+    uint32_t *G = (uint32_t *)work.p;
+    unsigned int *tickets = (unsigned int *)(G + 4 * 256);
+    uint32_t *flags = G + 4 * 256 + 4;
+    MCS_CUDA(cudaMemsetAsync(work.p, 0, words * sizeof(uint32_t), s));
+    k_rs_hist_all<<<ntiles, RS_THREADS, 0, s>>>(keys_a, T, G);
+    MCS_LAUNCH_CHECK();
+    for (int pass = 0; pass < 4; ++pass) {
+        const bool fwd = (pass & 1) == 0;
+        k_rs_pass<<<ntiles, RS_THREADS, 0, s>>>(fwd ? keys_a : keys_b, fwd ? vals_a : vals_b, fwd ? keys_b : keys_a, fwd ? vals_b : vals_a, T, pass, G, tickets + pass,
+                                               flags + (size_t)pass * ntiles * 256);
+        MCS_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 __device__ __forceinline__ int lbvh_delta(const uint32_t *__restrict__ k, int n, int i, int j)
 {
     if (j < 0 || j >= n) return -1;
@@ -160,14 +300,21 @@ __global__ void __launch_bounds__(256) k_karras(const uint32_t *__restrict__ k, 
     if (i == 0) parent[0] = -1;
 }
 
-__global__ void __launch_bounds__(256) k_leaves_refit(const float *__restrict__ verts, const int32_t *__restrict__ tris, int T,
-                                                      const float *__restrict__ tlo, const float *__restrict__ thi,
-                                                      const int32_t *__restrict__ prim, const uint32_t *__restrict__ bounds,
-                                                      const int32_t *__restrict__ left, const int32_t *__restrict__ right, const int32_t *__restrict__ parent,
-                                                      float *lo, float *hi, int *flags, float4 *__restrict__ trirec)
+// Bottom-up refit with arrival counters.  The triangles under an LBVH node are consecutive in Morton order, so a CTA that owns
+// REFIT_THREADS consecutive leaves also owns every internal node whose range lies inside that span -- for those the publish / observe
+// fences only have to order memory for threads of the SAME CTA (fence.cta); a device-wide fence is paid only at the few nodes whose
+// range crosses a CTA boundary (the top ~log2(T / 1024) levels).  Round 1 fenced device-wide twice per level for every thread:
+// 237 us of the 465 us rebuild at 1 M triangles, 50 of 136 us at 7 k (profiles/r02_bvh_build.json).
+#define REFIT_THREADS 1024
+__global__ void __launch_bounds__(REFIT_THREADS) k_leaves_refit(const float *__restrict__ verts, const int32_t *__restrict__ tris, int T,
+                                                                const float *__restrict__ tlo, const float *__restrict__ thi,
+                                                                const int32_t *__restrict__ prim, const uint32_t *__restrict__ bounds,
+                                                                const int32_t *__restrict__ left, const int32_t *__restrict__ right, const int32_t *__restrict__ parent,
+                                                                const int2 *__restrict__ range, float *lo, float *hi, int *flags, float4 *__restrict__ trirec)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= T) return;
+    const int span_lo = blockIdx.x * blockDim.x, span_hi = span_lo + blockDim.x - 1;
     float ex = __fsub_rn(ord2f(bounds[9]), ord2f(bounds[6]));
     float ey = __fsub_rn(ord2f(bounds[10]), ord2f(bounds[7]));
     float ez = __fsub_rn(ord2f(bounds[11]), ord2f(bounds[8]));
@@ -194,11 +341,13 @@ __global__ void __launch_bounds__(256) k_leaves_refit(const float *__restrict__ 
     }
     if (T == 1) return;
     // bottom-up: the second thread to reach a node computes its box
-    __threadfence();
     int p = parent[node];
     while (p >= 0) {
+        const int2 rg = range[p];
+        const bool inside = rg.x >= span_lo && rg.y <= span_hi;      // every leaf under p belongs to this CTA
+        if (inside) __threadfence_block(); else __threadfence();     // publish the child box this thread wrote
         if (atomicAdd(flags + p, 1) == 0) return;
-        __threadfence();
+        if (inside) __threadfence_block(); else __threadfence();     // observe the sibling's box
         int lc = left[p], rc = right[p];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -207,7 +356,6 @@ __global__ void __launch_bounds__(256) k_leaves_refit(const float *__restrict__ 
             lo[3 * (size_t)p + a] = fminf(v0, v1);
             hi[3 * (size_t)p + a] = fmaxf(w0, w1);
         }
-        __threadfence();
         p = parent[p];
     }
 }
@@ -405,18 +553,12 @@ int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris
     k_tri_bounds<<<nblk(T, 256), 256, 0, s>>>(verts, tris, T, tlo, thi, bounds);
     MCS_LAUNCH_CHECK();
     if (rebuild) {
-        // Measured and dropped for the small meshes (7-11 k triangles, where the radix sort is six latency-bound launches = 52 of the
-        // rebuild's 136 us of kernel time): a hand-written single-CTA shared-memory bitonic sort of 64-bit (key, id) composites -- correct
-        // (bit-identical structure) but 60-140 us on one SM; and the whole rebuild as ONE single-CTA launch -- 522 us (seven dependent
-        // gather / refit chains per thread instead of seven CTAs' worth of parallel ones).  profiles/r02_bvh_build.json.
-        k_morton<<<nblk(T, 256), 256, 0, s>>>(tlo, thi, T, bounds, (uint32_t *)c->keys.p, (int32_t *)c->vals.p);
+        // Measured and dropped for the small meshes (7-11 k triangles, where any multi-pass sort is latency-bound launches): a single-CTA
+        // shared-memory bitonic sort of 64-bit (key, id) composites -- bit-identical structure but 60-140 us on one SM; and the whole
+        // rebuild as ONE single-CTA launch -- 522 us (seven dependent gather / refit chains per thread).  profiles/r02_bvh_build.json.
+        k_morton<<<nblk(T, 256), 256, 0, s>>>(tlo, thi, T, bounds, (uint32_t *)c->keys_alt.p, (int32_t *)c->vals_alt.p);
         MCS_LAUNCH_CHECK();
-        size_t tmp_bytes = 0;
-        MCS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)c->keys.p, (uint32_t *)c->keys_alt.p,
-                                                 (const int32_t *)c->vals.p, (int32_t *)c->vals_alt.p, T, 0, 30, s));
-        if (int e = mcs_buf_reserve(c->sort_tmp, tmp_bytes, s)) return e;
-        MCS_CUDA(cub::DeviceRadixSort::SortPairs(c->sort_tmp.p, tmp_bytes, (const uint32_t *)c->keys.p, (uint32_t *)c->keys_alt.p,
-                                                 (const int32_t *)c->vals.p, (int32_t *)c->vals_alt.p, T, 0, 30, s));
+        if (int e = rs_sort_pairs((uint32_t *)c->keys_alt.p, (int32_t *)c->vals_alt.p, (uint32_t *)c->keys.p, (int32_t *)c->vals.p, T, c->sort_tmp, s)) return e;
         if (T > 1) {
             k_karras<<<nblk(T - 1, 256), 256, 0, s>>>((const uint32_t *)c->keys_alt.p, T, (int32_t *)c->left.p, (int32_t *)c->right.p, (int32_t *)c->parent.p,
                                                       (int2 *)c->range.p);
@@ -424,9 +566,9 @@ int mcs_bvh_build(mcs_ctx *c, const float *verts, int32_t V, const int32_t *tris
         }
     }
     MCS_CUDA(cudaMemsetAsync(c->flags.p, 0, nT * sizeof(int), s));
-    k_leaves_refit<<<nblk(T, 256), 256, 0, s>>>(verts, tris, T, tlo, thi, (const int32_t *)c->vals_alt.p, bounds, (const int32_t *)c->left.p,
-                                                (const int32_t *)c->right.p, (const int32_t *)c->parent.p, (float *)c->lo.p, (float *)c->hi.p,
-                                                (int *)c->flags.p, (float4 *)c->tris.p);
+    k_leaves_refit<<<nblk(T, REFIT_THREADS), REFIT_THREADS, 0, s>>>(verts, tris, T, tlo, thi, (const int32_t *)c->vals_alt.p, bounds, (const int32_t *)c->left.p,
+                                                                   (const int32_t *)c->right.p, (const int32_t *)c->parent.p, (const int2 *)c->range.p,
+                                                                   (float *)c->lo.p, (float *)c->hi.p, (int *)c->flags.p, (float4 *)c->tris.p);
     MCS_LAUNCH_CHECK();
     k_emit_both<<<nblk(T > 1 ? T - 1 : 1, 256), 256, 0, s>>>(T, (const int32_t *)c->left.p, (const int32_t *)c->right.p, (const int2 *)c->range.p,
                                                               (const float *)c->lo.p, (const float *)c->hi.p, (float4 *)c->nodes.p, (uint4 *)c->nodesq4.p,
