@@ -93,3 +93,44 @@ def test_denoise_and_combine_matches_the_unfused_tail(dev, bsdf):
             assert a.grad is None or float(a.grad.abs().max()) == 0
             continue
         assert rel_l2(a.grad.cpu().numpy(), b.grad.cpu().numpy()) < 1e-5, name
+
+
+@pytest.mark.parametrize("sigma", [2.0, 0.6, 0.0001])
+@pytest.mark.parametrize("shape", [(2, 45, 72), (1, 130, 256)])
+def test_tma_staged_forward(dev, sigma, shape):
+    """Contiguous [B,H,W,3] signals / normals, [B,H,W,2] depth and W % 4 == 0 take the TMA-staged forward kernel (denoise.cu:
+    bilateral_fwd_tma_kernel: cp.async.bulk.tensor.3d halo tiles, out-of-image taps zero-filled by the copy engine); a channel slice of
+    a wider tensor (12-byte pixels at a 16-byte pitch) cannot be described by a tensor map and takes the plain kernel.  Same tap loop:
+    the two must agree BIT FOR BIT, and with the oracle to 1e-4, for the single- and the two-signal entry points."""
+    import nvdiffrecmc_b200.optixutils as ou
+    from nvdiffrecmc_b200.optixutils.ops import _bilateral_denoiser_func, _bilateral_denoiser2_func
+    col, nrm, zdz = _inputs(*shape, seed=7 + int(sigma * 10))
+    colB = np.random.default_rng(3).uniform(0, 1, size=col.shape).astype(np.float32)
+    c, cb, n, z = [torch.tensor(x, device=dev) for x in (col, colB, nrm, zdz)]
+    pad = lambda t: torch.cat([t, torch.zeros_like(t[..., :1])], -1)[..., :3]            # same values, pixel pitch 16 B: not TMA-able
+    assert not pad(c).is_contiguous()
+    raw_tma = _bilateral_denoiser_func.apply(c, n, z, sigma)
+    raw_plain = _bilateral_denoiser_func.apply(pad(c), n, z, sigma)
+    assert torch.equal(raw_tma, raw_plain)
+    a_t, b_t = _bilateral_denoiser2_func.apply(c, cb, n, z, sigma)
+    a_p, b_p = _bilateral_denoiser2_func.apply(pad(c), pad(cb), n, z, sigma)
+    assert torch.equal(a_t, a_p) and torch.equal(b_t, b_p) and torch.equal(a_t, raw_tma)
+    ref = oracle().bilateral_fwd(col, nrm, zdz, sigma)
+    assert rel_l2(raw_tma.cpu().numpy(), ref) < TOL
+    # transposed filter: contiguous [B,H,W,4] upstream gradients take the TMA kernel (one 128-bit shared load per tap), a strided view the plain one
+    from nvdiffrecmc_b200 import _lib as L
+    import ctypes as C
+    g4 = torch.rand(*shape, 4, device=dev); g4b = torch.rand(*shape, 4, device=dev)
+    wide = lambda t: torch.cat([t, torch.zeros_like(t[..., :1])], -1)[..., :4]
+    outs = {}
+    for tag, (ga, gb) in (("tma", (g4, g4b)), ("plain", (wide(g4), wide(g4b)))):
+        ca = torch.empty(*shape, 3, device=dev); cb2 = torch.empty(*shape, 3, device=dev)
+        L.check(L.lib().mcs_bilateral_bwd2(C.byref(L.nhwc(n)), C.byref(L.nhwc(z)), float(sigma), C.byref(L.nhwc(ga)), C.byref(L.nhwc(gb)), ca.data_ptr(), cb2.data_ptr(),
+                                           L.stream_ptr()), "bilateral_denoiser2 (backward)")
+        c1 = torch.empty(*shape, 3, device=dev)
+        L.check(L.lib().mcs_bilateral_bwd(C.byref(L.nhwc(n)), C.byref(L.nhwc(z)), float(sigma), C.byref(L.nhwc(ga)), c1.data_ptr(), L.stream_ptr()), "bilateral_denoiser (backward)")
+        outs[tag] = (ca, cb2, c1)
+    for a, b in zip(outs["tma"], outs["plain"]):
+        assert torch.equal(a, b)
+    assert torch.equal(outs["tma"][0], outs["tma"][2])
+    assert rel_l2(outs["tma"][0].cpu().numpy(), oracle().bilateral_bwd(nrm, zdz, sigma, g4.cpu().numpy())) < TOL
