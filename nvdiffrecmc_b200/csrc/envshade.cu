@@ -281,6 +281,9 @@ __device__ __forceinline__ float warp_sum(float v)
 #ifndef MCS_CTA_WARPS
 #define MCS_CTA_WARPS 8
 #endif
+#ifndef MCS_STREAM_RECORD
+#define MCS_STREAM_RECORD 1
+#endif
 #ifndef MCS_SPLIT_WALKS
 #define MCS_SPLIT_WALKS 1
 #endif
@@ -830,8 +833,14 @@ __global__ void __launch_bounds__(NW * 32, 32 / NW) env_shade_kernel(const EnvPa
                     for (int k = lane; k < vn; k += 32) {
                         const int e = q.vlist[qb + k];
                         const int o = rec_off + k;
+#if MCS_STREAM_RECORD
+                        // streaming stores (evict-first): 1.8 GB of record per launch must not push the BVH / probe tables out of the L2
+                        __stcs(rr + o, q.dx[e]); __stcs(rr + p.rec_slots + o, q.dy[e]); __stcs(rr + 2 * p.rec_slots + o, q.dz[e]);
+                        __stcs(rr + 3 * p.rec_slots + o, q.mis[e]); __stcs(rr + 4 * p.rec_slots + o, __uint_as_float(q.tex[e]));
+#else
                         rr[o] = q.dx[e]; rr[p.rec_slots + o] = q.dy[e]; rr[2 * p.rec_slots + o] = q.dz[e]; rr[3 * p.rec_slots + o] = q.mis[e];
                         rr[4 * p.rec_slots + o] = __uint_as_float(q.tex[e]);
+#endif
                     }
                     rec_off += vn;
                     if (sub == nsub - 1 && lane == 0) p.rec_count[mypx] = (uint32_t)rec_off;
@@ -948,9 +957,15 @@ __global__ void __launch_bounds__(256, MCS_REPLAY_MINB) env_shade_replay_kernel(
             const float *rr = p.rec_rays + (size_t)pix * 5 * p.rec_slots;
             f3 g_kd = F3(0.0f), g_ks = F3(0.0f), g_nrm = F3(0.0f), g_wo = F3(0.0f);
             for (int k = lane; k < cnt; k += 32) {
+#if MCS_STREAM_RECORD
+                const f3 wi = F3(__ldcs(rr + k), __ldcs(rr + p.rec_slots + k), __ldcs(rr + 2 * p.rec_slots + k));
+                const float mis = __ldcs(rr + 3 * p.rec_slots + k);
+                const uint32_t tex = __float_as_uint(__ldcs(rr + 4 * p.rec_slots + k));
+#else
                 const f3 wi = F3(__ldg(rr + k), __ldg(rr + p.rec_slots + k), __ldg(rr + 2 * p.rec_slots + k));
                 const float mis = __ldg(rr + 3 * p.rec_slots + k);
                 const uint32_t tex = __float_as_uint(__ldg(rr + 4 * p.rec_slots + k));
+#endif
                 const int tx = tex & 0xFFFFu, ty = (tex >> 16) & 0x7FFFu;
                 const float wgt = ((tex >> 31) ? v_occluded : 1.0f) * mis * p.sample_frac;
                 const float *lp = p.light + (size_t)ty * p.l_s1 + (size_t)tx * p.l_s2;

@@ -42,13 +42,17 @@ def test_dominant_kernel_profile_is_per_config():
     import bench
     wl = dict(bench.WORKLOAD)
     assert bench.config_key(wl, 8) == "8x512x512_n8_blob+torus4_light256"
-    other = dict(wl, res=800)
-    assert bench.dominant_kernel_profile(other, 8) is None
-    prof = bench.dominant_kernel_profile(wl, 8)
-    if prof is not None:
-        for k in ("thread_inst_per_launch", "dram_bytes_per_launch", "rays_per_launch", "source"):
-            assert k in prof, k
-        assert prof["source"].startswith("profiles/")
+    assert bench.dominant_kernel_profile(dict(wl, res=640), 8) is None          # no capture committed for this configuration
+    assert bench.dominant_kernel_profile(dict(wl, n_samples_x=4), 8) is None
+    seen = {}
+    for w_, views in ((wl, 8), (dict(wl, res=800), 8), (dict(wl, res=1024, n_samples_x=16, mesh="grid1m", mesh_level=0), 1)):
+        prof = bench.dominant_kernel_profile(w_, views)
+        if prof is not None:
+            for k in ("thread_inst_per_launch", "dram_bytes_per_launch", "rays_per_launch", "source"):
+                assert k in prof, k
+            assert prof["source"].startswith("profiles/")
+            seen[bench.config_key(w_, views)] = prof["dram_bytes_per_launch"]
+    assert len(set(seen.values())) == len(seen), "every configuration carries ITS OWN capture"
 
 
 def test_coverage_balanced_deal():
