@@ -3,8 +3,8 @@
 // Replaces optix_build_bvh -> optixAccelBuild (render/optixutils/c_src/torch_bindings.cpp:37-116),
 // which the training loop calls EVERY iteration (geometry/dlmesh.py:50, dmtet.py:202).  The
 // reference cudaFree/cudaMalloc's its buffers per call and builds on legacy stream 0; here the
-// whole build is 7 small kernels + one radix sort on the caller's stream, no host sync, no
-// allocation in steady state (ctx.h).
+// whole build is 11 hand-written launches on the caller's stream (incl. the onesweep radix sort), no host sync, no
+// allocation in steady state (ctx.h), no library code.
 //
 // Pipeline (canonical, bit-identical to oracle/mcoracle.c:orc_lbvh_build so the integer structure
 // can be compared exactly):

@@ -5,8 +5,9 @@
 // B200 design (compute-bound: (2r+1)^2 = 529 taps/px at sigma = 2, only 48 B/px of compulsory HBM
 // traffic):
 //   * one CTA = 32x16 output pixels, the (32+2r)x(16+2r) halo tile of guides (normal, depth,
-//     depth-gradient) and signals staged ONCE in shared memory as SoA planes (conflict-free: a warp
-//     reads 32 consecutive floats of a plane row);
+//     depth-gradient) and signals staged ONCE in shared memory: by the TMA unit as AoS tiles when the operands are contiguous
+//     (bilateral_tma_kernel below: the path render.shade()'s fused tail and bench.py take), else by plain loads as SoA planes
+//     (bilateral_kernel: strided channel slices; conflict-free: a warp reads 32 consecutive floats of a plane row);
 //   * each thread produces two vertically adjacent outputs so every tap value read from shared
 //     memory is used twice (halves LDS traffic, the co-limiter next to the FP32/MUFU pipes);
 //   * the spatial gaussian exponent is one FMA on a running tap offset; gaussian and depth term are merged into ONE

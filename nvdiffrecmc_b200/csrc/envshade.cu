@@ -10,11 +10,13 @@
 //      v3 deferred leaf tests, 25/32 lanes but 22 % instruction-fetch stalls with 32 independent warps spread over all
 //      phases; v4 one 32-warp CTA per SM in lock-step phases: no fetch stalls, L1 hit 88 %; final: 4 CTAs x 8 warps, so that
 //      one CTA's ALU-heavy generate phase overlaps another's latency-heavy trace phase, +9 %):
-//       G  generate: every warp draws the 2N^2 samples of its pixel (exact path, all lanes); rays that can contribute
-//          (n.wi > 0) are ballot-compacted into the warp's segment of a block-wide shared-memory queue (direction, env
-//          texel, MIS weight);
+//       G  generate, in two stages (round 2): every warp draws the directions of the 2N^2 samples of its pixel (exact path, all
+//          lanes); rays that can contribute (n.wi > 0) are ballot-compacted into the warp's segment of a block-wide shared-memory
+//          queue; the rest of the set-up (lat-long texel, light and BSDF pdf -> MIS weight) runs on the compacted entries only;
 //       T  trace: all warps drain the queue together -- own segment first, then work stealing -- with one 4-wide quantised
-//          BVH node step per lane per iteration (v6), leaf tests deferred to full-warp batches, dynamic ray fetch; one bit per ray;
+//          BVH node step per lane per iteration (v6), leaf tests deferred to full-warp batches, dynamic ray fetch (a ray is picked up
+//          with three MUFU.RCP: the culling constants are not part of the parity contract), and, once the queue is empty, idle lanes
+//          take over pending subtrees of the walks still in flight (round 2); one bit per ray;
 //       E  evaluate: each warp compacts the surviving rays (V != 0) of its pixel and only those evaluate the BSDF (forward)
 //          or its adjoint + the env-map gradient scatter (backward); warp-shuffle reduction, one writer per pixel.
 //     The reference runs one thread per pixel and loops 2*N^2 samples serially with an optixTrace per sample.
@@ -539,8 +541,13 @@ __device__ __forceinline__ void gen_segment(const EnvParams &p, BlockQueue &q, B
 //     (tex bit 31), which the owning lane polls after each batch to abandon the walk;
 //   * a lane whose walk ends pulls the next ray -- from the warp's own segment first, then from the other warps' segments --
 //     as soon as fewer than REFILL_BELOW lanes are busy;
+//   * when nothing is left to pull (the drain of a batch: the long walks), idle lanes are handed the BOTTOM stack entry of busy lanes
+//     and walk that subtree for the same ray (MCS_SPLIT_WALKS);
 //   * visibility of a ray = its occluded bit after all segments AND all pending lists have drained (block barrier).
-// What bounds it (profiles/r01_v6_*): instruction issue (73 % of peak, ~22 of 32 lanes).  With fp32 64-byte binary nodes (4 loads
+// One visit = ~100 SASS instructions (round 1: ~150): raw prmt plane decode with six selector registers, no comparison relax, leaf
+// flags from the node word, unconditional child stores with a conditional stack-pointer bump.
+// What bounds it (profiles/r02_envshade_*): instruction issue + latency (73 % issue-active, 24 of 32 lanes = 54 % of the
+// thread-instruction peak; no pipe above 60 %).  With fp32 64-byte binary nodes (4 loads
 // per visit) the L1 data pipe was a co-limiter at 75 %; quantised nodes took it to 47 % and long-scoreboard stalls from 25 % to
 // 18 % at equal run time; the 4-wide view then halves the visits (13.8 vs 28.8 per ray) for -8 % run time.  Measured and
 // rejected: 4-wide fp32 nodes (7 loads per visit: L1-bound, +5 %), node fetch through the texture path (equal), per-node
