@@ -327,3 +327,51 @@ def test_product_against_frozen_reference_outputs(dev, tag, bsdf):
             assert np.abs(got).max() == 0, name
         else:
             assert rel_l2(got, r) < 1e-3, (name, rel_l2(got, r))                # the frozen side is fp32: noise floor 2-5e-4 on the GGX adjoints
+
+
+def test_device_resident_seed(dev):
+    """rnd_seed may be a 1-element CUDA int32 tensor (C ABI: seed_offset_dev): the kernel reads it when it RUNS, so a CUDA-graph-captured
+    step can advance the seed in-graph (render.py:116 bumps a host counter).  Same rays as the host seed of equal value, forward and in
+    all three backward modes; a graph captured once follows the tensor."""
+    import nvdiffrecmc_b200.optixutils as ou
+    from nvdiffrecmc_b200.optixutils import ops
+    N = 4
+    c = make_case(res=16, B=2, N=N, seed=9)
+    ctx = _ctx(c, dev)
+    perms = _t(c, "perms", dev)
+    seed_t = torch.full((1,), 7, dtype=torch.int32, device=dev)
+
+    def run(seed, replay):
+        default = ops.HIT_RECORD_REPLAY
+        ops.HIT_RECORD_REPLAY = replay
+        try:
+            mask, ro, pos, nrm, view, kd, ks, light, pdf, rows, cols = _args(c, dev)
+            for x in (pos, nrm, kd, ks, light):
+                x.requires_grad_(True)
+            d, s = ou.optix_env_shade(ctx, mask, ro, pos, nrm, view, kd, ks, light, pdf, rows, cols, n_samples_x=N, rnd_seed=seed, perms=perms)
+            (d.sum() + (s * s).sum()).backward()
+            return d.detach(), s.detach(), kd.grad.clone(), light.grad.clone()
+        finally:
+            ops.HIT_RECORD_REPLAY = default
+    for replay in ("rays", "bits", None):
+        a, b = run(7, replay), run(seed_t, replay)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+        assert rel_l2(b[3].cpu().numpy(), a[3].cpu().numpy()) < 1e-6              # env-map gradient: atomics reorder
+    seed_t += 1
+    a, b = run(8, "rays"), run(seed_t, "rays")
+    assert torch.equal(a[0], b[0]) and not torch.equal(a[0], run(7, "rays")[0])
+    with pytest.raises(RuntimeError, match="1-element CUDA int32"):
+        ou.optix_env_shade(ctx, *_args(c, dev), n_samples_x=N, rnd_seed=torch.zeros(1, dtype=torch.int64, device=dev), perms=perms)
+    # one captured forward launch, replayed with an advancing device seed
+    args = _args(c, dev)
+    seed_g = torch.full((1,), 20, dtype=torch.int32, device=dev)
+    ou.optix_env_shade(ctx, *args, n_samples_x=N, rnd_seed=seed_g, perms=perms)      # warm up outside capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        seed_g += 1
+        dg, sg = ou.optix_env_shade(ctx, *args, n_samples_x=N, rnd_seed=seed_g, perms=perms)
+    for k in (1, 2):
+        g.replay()
+        ref = ou.optix_env_shade(ctx, *args, n_samples_x=N, rnd_seed=20 + k, perms=perms)      # capture records, it does not execute
+        assert torch.equal(dg, ref[0]) and torch.equal(sg, ref[1]), k

@@ -127,3 +127,15 @@ def test_image_loss_rejects_unknown_names():
         with pytest.raises(ValueError, match="unknown"):
             ru.image_loss(x, x, **kw)                              # native path: rejected before any device work
     assert float(ru.image_loss(x, x, loss="n2n", tonemapper="log_srgb", use_python=True)) == 0.0
+
+
+def test_seed_tensor_validation_and_bucket_adopt_errors():
+    from nvdiffrecmc_b200.optixutils.ops import _split_seed
+    from nvdiffrecmc_b200.parallel import GradBucket
+    assert _split_seed(5) == (5, None) and _split_seed(-1)[0] == 0xFFFFFFFF
+    with pytest.raises(RuntimeError, match="1-element CUDA int32"):
+        _split_seed(torch.zeros(1, dtype=torch.int32))                 # a CPU tensor is not a device-resident seed
+    with pytest.raises(ValueError, match="no trainable"):
+        GradBucket.adopt([torch.zeros(3)])
+    with pytest.raises(ValueError, match="share device and dtype"):
+        GradBucket.adopt([torch.zeros(3, requires_grad=True), torch.zeros(3, dtype=torch.float64, requires_grad=True)])
