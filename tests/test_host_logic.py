@@ -139,3 +139,16 @@ def test_seed_tensor_validation_and_bucket_adopt_errors():
         GradBucket.adopt([torch.zeros(3)])
     with pytest.raises(ValueError, match="share device and dtype"):
         GradBucket.adopt([torch.zeros(3, requires_grad=True), torch.zeros(3, dtype=torch.float64, requires_grad=True)])
+
+
+def test_every_profile_file_the_documents_cite_exists():
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    missing = []
+    for doc in ("DESIGN.md", "README.md", "INTEGRATION.md", os.path.join("profiles", "README.md")):
+        text = open(os.path.join(root, doc)).read()
+        for m in set(re.findall(r"((?:profiles/)?r0[12]_[A-Za-z0-9_]+\.(?:json|csv|txt))", text)):
+            if not os.path.exists(os.path.join(root, "profiles", m.replace("profiles/", ""))):
+                missing.append((doc, m))
+    assert not missing, missing
