@@ -490,6 +490,29 @@ def cpu_case(o, wl, res_s):
     return case
 
 
+REF_SAMPLE_RES = 128
+
+
+def make_config(wl, views, world):
+    """`config` of the JSON line -- identical for the product arm and the `--impl reference` arm (everything in it follows from the
+    workload definition; measured quantities go to `workload_measured`)."""
+    N, res, lr, tr = wl["n_samples_x"], wl["res"], wl["light_res"], wl["tex_res"]
+    bucket_mb = (lr * lr * 3 + 2 * tr * tr * 3) * 4 / 1e6
+    gbuf_mb = views * (res * res * 64 + 12) / 1e6          # mask 4 + pos / smooth_nrm / tangent / geom_nrm 12 each + depth 4 + texel index 8 B per pixel
+    return {"workload": wl["name"], "views_per_gpu": views, "global_views": views * world, "res": res, "n_samples_x": N,
+            "rays_per_covered_pixel": 2 * N * N,
+            "step": "dataset reference render (fwd only, %dx%d HDR probe, metal material; dataset_mesh.py:108-110) -> update_pdf -> LBVH rebuild -> "
+                    "shade (texel fetch, shading normal, env_shade, fused denoise + recombine) -> log-sRGB L1 loss -> backward -> all-reduce -> Adam + clamps"
+                    % (wl["ref_light_hw"][0], wl["ref_light_hw"][1]),
+            "trainable_probe": "%dx%d U[0.25,0.75) (create_trainable_env_rnd, light.py:98-101); the HDR-initialised probe is in `hdr_probe`" % (lr, lr),
+            "parallelism": "dp%d over views (coverage-balanced deal of the global batch), one NCCL all-reduce of the flat gradient bucket (%.1f MB) via "
+                           "parallel.GradBucket + hook_optimizer" % (world, bucket_mb),
+            "l2_policy": "per-step inputs (G-buffer %.0f MB + intermediates) exceed the 126 MB L2" % gbuf_mb,
+            "reference_arm_sampling": "`--impl reference` times the same step on the host cores on a BOUNDED SAMPLE of this workload (1 view at %dx%d of the "
+                                      "same scene, probes, n_samples_x, sigma) and reports the size-normalised Mrays/s; its ms_per_step is per sample step"
+                                      % (REF_SAMPLE_RES, REF_SAMPLE_RES)}
+
+
 PASSES = 3      # env_shade passes per training iteration as the reference runs it: dataset reference render (fwd), shade fwd, shade bwd (re-trace)
 
 
@@ -546,7 +569,7 @@ def run_reference(args, wl):
     o = oracle()
     cores = o.set_threads(cores)
     es, kind = cpu_reference(o)
-    N, res_s = wl["n_samples_x"], 128
+    N, res_s = wl["n_samples_x"], REF_SAMPLE_RES
     case = cpu_case(o, wl, res_s)
     covered = int((case["mask"] > 0).sum())
     rays_step = covered * 2 * N * N * PASSES
@@ -562,8 +585,9 @@ def run_reference(args, wl):
         "impl": "reference", "metric": "shadow_rays_per_second_train_step", "value": round(val, 4), "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "reference_arm": REF_ARM_NOTE[kind],
-                   "sample": "BOUNDED SAMPLE, not the full workload: " + sample + "; Mrays/s is size-normalised, ms_per_step is per SAMPLE step"},
+        "config": make_config(wl, wl["views_per_gpu"], max(int(args.gpus), 1)),
+        "reference_arm": REF_ARM_NOTE[kind],
+        "reference_sample": "BOUNDED SAMPLE, not the full workload: " + sample + "; Mrays/s is size-normalised, ms_per_step is per SAMPLE step",
         "cpu_baseline": {"value": round(val, 4), "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": round(val, 4), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "iters_per_s_on_sample": round(1.0 / dt, 4),
@@ -946,16 +970,9 @@ def main():
         "metric": "shadow_rays_per_second_train_step", "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "views_per_gpu": main_views, "global_views": main_views * world, "res": wl["res"],
-                   "n_samples_x": N, "rays_per_covered_pixel": 2 * N * N, "covered_pixels_rank0": w.covered,
-                   "coverage_rank0": round(w.covered / (main_views * wl["res"] ** 2), 4),
-                   "rays_per_pass_min_max_over_ranks": [int(rays_min), int(rays_max)],
-                   "step": "dataset reference render (fwd only, 1024x2048 HDR probe, metal material; dataset_mesh.py:108-110) -> update_pdf -> LBVH rebuild -> "
-                           "shade (texel fetch, shading normal, env_shade, fused denoise + recombine) -> log-sRGB L1 loss -> backward -> all-reduce -> Adam + clamps",
-                   "trainable_probe": "%dx%d U[0.25,0.75) (create_trainable_env_rnd, light.py:98-101); the HDR-initialised probe is in `hdr_probe`" % (wl["light_res"], wl["light_res"]),
-                   "parallelism": "dp%d over views (coverage-balanced deal of the global batch), one NCCL all-reduce of the flat gradient bucket (%.1f MB) via "
-                                  "parallel.GradBucket + hook_optimizer" % (world, w.flat_grad.numel() * 4 / 1e6),
-                   "l2_policy": "per-step inputs (G-buffer %.0f MB + intermediates) exceed the 126 MB L2" % (w.bytes_h2d / 1e6)},
+        "config": make_config(wl, main_views, world),
+        "workload_measured": {"covered_pixels_rank0": w.covered, "coverage_rank0": round(w.covered / (main_views * wl["res"] ** 2), 4),
+                              "rays_per_pass_min_max_over_ranks": [int(rays_min), int(rays_max)], "h2d_bytes_per_step": int(w.bytes_h2d)},
         "rays_counted": "covered px x 2N^2 per pass x %d passes, as the reference traces them (dataset reference render, shade forward, shade backward re-trace); "
                         "here the two forward passes trace (skipping rays with n.wi<=0, exactly-zero contribution) and the backward replays the forward's ray record: "
                         "see value_traced" % PASSES,

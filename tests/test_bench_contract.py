@@ -26,6 +26,10 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
     import bench
     assert d["cpu_baseline"]["cores"] == bench.host_cores()     # not the 1 thread of the inherited OMP_NUM_THREADS
+    # the reference arm reports on the PRODUCT arm's config (both lines build it with bench.make_config); the bounded sample it actually
+    # times is stated inside that config and, with its ray count, in cpu_baseline.sample / reference_sample
+    assert d["config"] == bench.make_config(dict(bench.WORKLOAD), bench.WORKLOAD["views_per_gpu"], 1)
+    assert "BOUNDED SAMPLE" in d["config"]["reference_arm_sampling"] and "BOUNDED SAMPLE" in d["reference_sample"]
 
 
 def test_non_zero_ranks_of_the_reference_arm_stay_silent():
